@@ -1,0 +1,135 @@
+"""In-tree builder for the two native libraries.
+
+* ``_host``  – pybind11 module (g++ only): formats, codecs, slicers, tokenizer, sampler.
+* ``_cuda``  – plain C-ABI shared library (nvcc, sm_100a only): kernels, engine runtime, peer-memory comm.
+  Loaded through ctypes so the kernels carry no torch/pybind dependency and compile in seconds.
+
+Artifacts are written next to this file (git-ignored, but shipped to the GPU box by gpurun).
+A source hash is stored beside each artifact so stale builds are rebuilt and fresh ones are reused.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+import sysconfig
+import threading
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_DIR = PKG_DIR.parent
+CSRC = REPO_DIR / "csrc"
+_lock = threading.Lock()
+
+NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _hash_sources(files, extra: str = "") -> str:
+    h = hashlib.sha256(extra.encode())
+    for f in sorted(files):
+        h.update(str(f.name).encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()
+
+
+def _run(cmd, cwd=None):
+    proc = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("build command failed:\n  " + " ".join(map(str, cmd)) + "\n" + proc.stdout)
+    return proc.stdout
+
+
+def host_lib_path() -> Path:
+    return PKG_DIR / ("_host" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def cuda_lib_path() -> Path:
+    return PKG_DIR / "_cuda.so"
+
+
+def build_host(force: bool = False, verbose: bool = False) -> Path:
+    src_dir = CSRC / "host"
+    sources = sorted(src_dir.glob("*.cpp"))
+    headers = sorted(src_dir.glob("*.hpp"))
+    out = host_lib_path()
+    stamp = out.with_suffix(out.suffix + ".hash")
+    flags = ["-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-Wno-sign-compare"]
+    digest = _hash_sources(sources + headers, " ".join(flags))
+    with _lock:
+        if not force and out.exists() and stamp.exists() and stamp.read_text() == digest:
+            return out
+        import pybind11
+
+        inc = ["-I" + sysconfig.get_paths()["include"], "-I" + pybind11.get_include()]
+        tmp = out.with_suffix(".tmp.so")
+        cmd = ["g++", *flags, *inc, *map(str, sources), "-o", str(tmp)]
+        log = _run(cmd)
+        if verbose and log:
+            print(log)
+        os.replace(tmp, out)
+        stamp.write_text(digest)
+    return out
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> Path:
+    src_dir = CSRC / "cuda"
+    sources = sorted(src_dir.glob("*.cu"))
+    headers = sorted(src_dir.glob("*.cuh")) + sorted(src_dir.glob("*.h"))
+    out = cuda_lib_path()
+    stamp = out.with_suffix(".so.hash")
+    flags = [*NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC",
+             "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+    digest = _hash_sources(sources + headers, " ".join(flags))
+    with _lock:
+        if not force and out.exists() and stamp.exists() and stamp.read_text() == digest:
+            return out
+        nvcc = nvcc_path()
+        obj_dir = REPO_DIR / "build" / "cuda"
+        obj_dir.mkdir(parents=True, exist_ok=True)
+        objs = []
+        procs = []
+        for s in sources:
+            o = obj_dir / (s.stem + ".o")
+            objs.append(o)
+            ostamp = o.with_suffix(".o.hash")
+            odigest = _hash_sources([s] + headers, " ".join(flags))
+            if not force and o.exists() and ostamp.exists() and ostamp.read_text() == odigest:
+                continue
+            cmd = [nvcc, *flags, "-c", str(s), "-o", str(o)]
+            procs.append((s, o, ostamp, odigest, cmd,
+                          subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        logs = []
+        for s, o, ostamp, odigest, cmd, p in procs:
+            text, _ = p.communicate()
+            logs.append(f"== {s.name}\n{text}")
+            if p.returncode != 0:
+                raise RuntimeError("nvcc failed:\n  " + " ".join(cmd) + "\n" + text)
+            ostamp.write_text(odigest)
+        (obj_dir / "ptxas.log").write_text("\n".join(logs))
+        if verbose:
+            print("\n".join(logs))
+        tmp = out.with_suffix(".tmp.so")
+        _run([nvcc, *NVCC_ARCH, "-shared", "-o", str(tmp), *map(str, objs)])
+        os.replace(tmp, out)
+        stamp.write_text(digest)
+    return out
+
+
+def build_all(force: bool = False, verbose: bool = False):
+    return build_host(force, verbose), build_cuda(force, verbose)
+
+
+if __name__ == "__main__":
+    force = "--force" in sys.argv
+    h, c = build_all(force=force, verbose="-v" in sys.argv)
+    print(h)
+    print(c)
