@@ -1,0 +1,193 @@
+// Per-rank inference engine: owns the kernel schedule of one forward pass and the CUDA graph of the decode step.
+//
+// Role in the reference: NnExecutor + NnCpuDevice/NnVulkanDevice + the `start/att/ff/end` segments emitted by
+// buildLlmNet (src/nn/nn-executor.cpp:45-207, src/llm.cpp:247-603) — ~26 barrier-separated ops per layer driven
+// by an interpreter. Here a forward pass is a fixed sequence of 5 fused kernels per layer, chained with
+// programmatic dependent launch, and the single-token step is captured once into a CUDA graph whose inputs
+// (token id, position) live in device memory so the graph replays without host round trips:
+// the sampling kernel writes the next token and advances the position on the device.
+#include <vector>
+
+#include "kernels.h"
+
+namespace dl {
+
+struct EngineConfig {   // mirrored by ctypes in distributed_llama_b200/ops/cuda_lib.py
+    uint32_t dim, nLayers, nHeads, nKvHeads, headDim, ffDim, vocab, seqLen;   // per-rank (sliced) head/ff/vocab counts
+    uint32_t nExperts, nActiveExperts;
+    uint32_t maxBatch;       // tokens per forward on the GEMV path
+    uint32_t nSplits;        // attention KV splits
+    uint32_t rank, nRanks;
+    uint32_t numSms;
+    float eps;
+    uint32_t usePdl;
+};
+
+struct LayerPtrs {
+    const void *qkvQs, *qkvSc;   // [(nHeads+2nKvHeads)*hd][dim]
+    const void *woQs, *woSc;     // [dim][nHeads*hd]
+    const void *w13Qs, *w13Sc;   // [2*ff][dim] (gate/up interleaved); MoE: [nExperts][2*ff][dim]
+    const void *w2Qs, *w2Sc;     // [dim][ff];                          MoE: [nExperts][dim][ff]
+    const float *norm0, *norm1, *qNorm, *kNorm;
+    const float *moeGate;        // [nExperts][dim] f32
+    void *kCache, *vCache;       // bf16 [nKvHeads][seqLen][hd]
+};
+
+struct GlobalPtrs {
+    const float *embedding;      // [vocabFull][dim]
+    const float *finalNorm;
+    const void *wclsQs, *wclsSc; // [vocab][dim]
+    const float *rope;           // [seqLen][hd/2][2]
+    uint32_t vocabFull;
+    // activations / state
+    int *tokens, *pos;           // [maxBatch]
+    float *x, *qkv, *z, *h, *logits;   // [maxBatch][dim | qkvDim | qDim | ff | vocab]
+    float *attnPartial;          // [maxBatch][nHeads][nSplits][hd+2]
+    unsigned int *attnCounters;  // [maxBatch][nHeads]
+    int *history;                // [seqLen] generated token per position (device-side log), may be null
+    // MoE scratch
+    int *expertIdx;              // [maxBatch][nActive]
+    float *expertWeight;         // [maxBatch][nActive]
+};
+
+struct Engine {
+    EngineConfig cfg{};
+    std::vector<LayerPtrs> layers;
+    GlobalPtrs g{};
+    cudaGraphExec_t decodeGraph = nullptr;
+    cudaStream_t captureStream = nullptr;
+    int lastError = 0;
+};
+
+#define DL_TRY(expr)                    \
+    do {                                \
+        const int _r = (expr);          \
+        if (_r != 0) return _r;         \
+    } while (0)
+
+// logitsMode: 0 = none (prefill chunk), 1 = logits of the last token in the batch into logits[0], 2 = all tokens
+static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, cudaStream_t stream) {
+    const EngineConfig &c = e.cfg;
+    const bool pdl = c.usePdl != 0;
+    const uint32_t qDim = c.nHeads * c.headDim, kvDim = c.nKvHeads * c.headDim, qkvDim = qDim + 2 * kvDim;
+    if (nb < 1 || (uint32_t)nb > c.maxBatch || (nb & (nb - 1))) return -10;
+
+    DL_TRY(launchEmbedding(e.g.embedding, e.g.tokens, e.g.x, c.dim, c.dim, e.g.vocabFull, nb, stream));
+    for (uint32_t l = 0; l < c.nLayers; l++) {
+        const LayerPtrs &L = e.layers[l];
+        GemvArgs a{};
+        // 1. rmsnorm -> q80 -> QKV
+        a.qs = (const uint32_t *)L.qkvQs; a.scales = (const __half *)L.qkvSc; a.d = qkvDim; a.n = c.dim;
+        a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm0; a.eps = c.eps; a.out = e.g.qkv; a.outStride = qkvDim;
+        DL_TRY(gemvQ40(PRO_RMSNORM_, EPI_STORE_, nb, a, c.numSms, stream, pdl));
+        // 2. qk-norm + rope + kv write
+        RopeKvArgs r{};
+        r.qkv = e.g.qkv; r.qkvStride = qkvDim; r.pos = e.g.pos; r.rope = e.g.rope; r.qNorm = L.qNorm; r.kNorm = L.kNorm;
+        r.eps = c.eps; r.nHeads = c.nHeads; r.nKvHeads = c.nKvHeads; r.headDim = c.headDim; r.seqLen = c.seqLen;
+        r.kCache = (__nv_bfloat16 *)L.kCache; r.vCache = (__nv_bfloat16 *)L.vCache;
+        DL_TRY(launchRopeKv(r, nb, stream, pdl));
+        // 3. attention
+        AttnArgs t{};
+        t.qkv = e.g.qkv; t.qkvStride = qkvDim; t.pos = e.g.pos; t.kCache = r.kCache; t.vCache = r.vCache;
+        t.nHeads = c.nHeads; t.nKvHeads = c.nKvHeads; t.headDim = c.headDim; t.seqLen = c.seqLen; t.nSplits = c.nSplits;
+        t.partial = e.g.attnPartial; t.counters = e.g.attnCounters; t.out = e.g.z; t.outStride = qDim;
+        DL_TRY(launchAttnDecode(t, nb, stream, pdl));
+        // 4. q80 -> WO, residual add
+        a = GemvArgs{};
+        a.qs = (const uint32_t *)L.woQs; a.scales = (const __half *)L.woSc; a.d = c.dim; a.n = qDim;
+        a.in = e.g.z; a.inStride = qDim; a.out = e.g.x; a.outStride = c.dim;
+        DL_TRY(gemvQ40(PRO_PLAIN_, EPI_RESIDUAL_, nb, a, c.numSms, stream, pdl));
+        // 5. rmsnorm -> q80 -> W1|W3 -> silu*up
+        a = GemvArgs{};
+        a.qs = (const uint32_t *)L.w13Qs; a.scales = (const __half *)L.w13Sc; a.d = 2 * c.ffDim; a.n = c.dim;
+        a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm1; a.eps = c.eps; a.out = e.g.h; a.outStride = c.ffDim;
+        DL_TRY(gemvQ40(PRO_RMSNORM_, EPI_SWIGLU_, nb, a, c.numSms, stream, pdl));
+        // 6. q80 -> W2, residual add
+        a = GemvArgs{};
+        a.qs = (const uint32_t *)L.w2Qs; a.scales = (const __half *)L.w2Sc; a.d = c.dim; a.n = c.ffDim;
+        a.in = e.g.h; a.inStride = c.ffDim; a.out = e.g.x; a.outStride = c.dim;
+        DL_TRY(gemvQ40(PRO_PLAIN_, EPI_RESIDUAL_, nb, a, c.numSms, stream, pdl));
+    }
+    if (logitsMode != 0) {
+        GemvArgs a{};
+        a.qs = (const uint32_t *)e.g.wclsQs; a.scales = (const __half *)e.g.wclsSc; a.d = c.vocab; a.n = c.dim;
+        a.normW = e.g.finalNorm; a.eps = c.eps; a.inStride = c.dim; a.outStride = c.vocab; a.out = e.g.logits;
+        if (logitsMode == 1) {
+            a.in = e.g.x + (size_t)(nb - 1) * c.dim;
+            DL_TRY(gemvQ40(PRO_RMSNORM_, EPI_STORE_, 1, a, c.numSms, stream, pdl));
+        } else {
+            a.in = e.g.x;
+            DL_TRY(gemvQ40(PRO_RMSNORM_, EPI_STORE_, nb, a, c.numSms, stream, pdl));
+        }
+        if (greedyAdvance)
+            DL_TRY(launchArgmaxAdvance(e.g.logits, c.vocab, e.g.tokens, e.g.pos, e.g.history, c.seqLen, stream, pdl));
+    }
+    return 0;
+}
+
+}  // namespace dl
+
+using dl::Engine;
+
+DL_EXPORT void *dl_engine_create(const dl::EngineConfig *cfg) {
+    Engine *e = new Engine();
+    e->cfg = *cfg;
+    e->layers.resize(cfg->nLayers);
+    if (e->cfg.numSms == 0) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e->cfg.numSms = (uint32_t)sms;
+    }
+    return e;
+}
+
+DL_EXPORT void dl_engine_destroy(void *h) {
+    Engine *e = (Engine *)h;
+    if (!e) return;
+    if (e->decodeGraph) cudaGraphExecDestroy(e->decodeGraph);
+    if (e->captureStream) cudaStreamDestroy(e->captureStream);
+    delete e;
+}
+
+DL_EXPORT int dl_engine_set_layer(void *h, uint32_t layer, const dl::LayerPtrs *p) {
+    Engine *e = (Engine *)h;
+    if (layer >= e->layers.size()) return -1;
+    e->layers[layer] = *p;
+    return 0;
+}
+
+DL_EXPORT int dl_engine_set_globals(void *h, const dl::GlobalPtrs *p) {
+    ((Engine *)h)->g = *p;
+    return 0;
+}
+
+DL_EXPORT uint32_t dl_engine_num_sms(void *h) { return ((Engine *)h)->cfg.numSms; }
+
+DL_EXPORT int dl_engine_forward(void *h, int nb, int logitsMode, int greedyAdvance, cudaStream_t stream) {
+    return dl::engineForward(*(Engine *)h, nb, logitsMode, greedyAdvance != 0, stream);
+}
+
+// Captures one greedy decode step (forward of 1 token + argmax + position advance) into a graph.
+DL_EXPORT int dl_engine_capture_decode(void *h) {
+    Engine *e = (Engine *)h;
+    if (!e->captureStream) DL_CUDA_CHECK(cudaStreamCreateWithFlags(&e->captureStream, cudaStreamNonBlocking));
+    if (e->decodeGraph) { cudaGraphExecDestroy(e->decodeGraph); e->decodeGraph = nullptr; }
+    DL_CUDA_CHECK(cudaStreamBeginCapture(e->captureStream, cudaStreamCaptureModeThreadLocal));
+    const int r = dl::engineForward(*e, 1, 1, true, e->captureStream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t endErr = cudaStreamEndCapture(e->captureStream, &graph);
+    if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
+    DL_CUDA_CHECK(endErr);
+    DL_CUDA_CHECK(cudaGraphInstantiate(&e->decodeGraph, graph, 0));
+    cudaGraphDestroy(graph);
+    return 0;
+}
+
+// Replays the captured step `nSteps` times back to back on `stream` (no host sync in between).
+DL_EXPORT int dl_engine_decode_graph(void *h, int nSteps, cudaStream_t stream) {
+    Engine *e = (Engine *)h;
+    if (!e->decodeGraph) return -20;
+    for (int i = 0; i < nSteps; i++) DL_CUDA_CHECK(cudaGraphLaunch(e->decodeGraph, stream));
+    return 0;
+}

@@ -1,0 +1,150 @@
+"""`.m` file -> device weights of one tensor-parallel rank.
+
+Reference behaviour replaced: loadLlmNetWeight + NnRootWeightLoader (src/llm.cpp:614-669,
+src/nn/nn-network.cpp:797-888): the root walks the file, splits every tensor on the CPU and streams the slices
+to workers over TCP. Here every rank maps the file, uploads the byte range that contains its rows and lets the
+`repack_q40` kernel cut the column slice and re-tile into the device layout on the GPU (see csrc/cuda/repack.cu).
+Partition rules are the reference's (row split for q,k,v,w1,w3,wcls; column split for wo,w2).
+
+Device-side fusions prepared here:
+  * q|k|v rows concatenated into one matrix  (one GEMV/GEMM per layer instead of three)
+  * w1/w3 rows interleaved (gate_i, up_i)     (SwiGLU in the epilogue of one kernel)
+  * NeoX/"Falcon" rotary layout (Qwen3) re-ordered to adjacent pairs at load, q_norm/k_norm permuted alike
+"""
+from __future__ import annotations
+
+import warnings
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import host
+from ..formats.model_file import ModelFile
+from ..formats import quants
+from ..ops.q40 import DeviceQ40, repack_q40
+from .config import ROPE_FALCON
+
+
+@dataclass
+class LayerWeights:
+    qkv: DeviceQ40
+    wo: DeviceQ40
+    w13: DeviceQ40
+    w2: DeviceQ40
+    norm0: torch.Tensor
+    norm1: torch.Tensor
+    q_norm: Optional[torch.Tensor] = None
+    k_norm: Optional[torch.Tensor] = None
+    moe_gate: Optional[torch.Tensor] = None
+
+
+@dataclass
+class DeviceWeights:
+    header: object
+    rank: int
+    n_ranks: int
+    n_heads: int          # local
+    n_kv_heads: int       # local
+    ff_dim: int           # local
+    vocab: int            # local
+    embedding: torch.Tensor
+    final_norm: torch.Tensor
+    wcls: DeviceQ40
+    rope: torch.Tensor
+    layers: List[LayerWeights] = field(default_factory=list)
+    bytes_uploaded: int = 0
+
+
+def _interleave_perm(head_dim: int) -> np.ndarray:
+    """new[2j] = old[j], new[2j+1] = old[j + hd/2]"""
+    half = head_dim // 2
+    perm = np.empty(head_dim, dtype=np.int64)
+    perm[0::2] = np.arange(half)
+    perm[1::2] = np.arange(half) + half
+    return perm
+
+
+class _Uploader:
+    def __init__(self, mf: ModelFile, device):
+        self.mf = mf
+        self.device = device
+        self.bytes = 0
+
+    def rows(self, entry, first_row: int, n_rows: int) -> torch.Tensor:
+        """Uploads full-width rows [first_row, first_row+n_rows) of a tensor as raw bytes."""
+        row_bytes = quants.tensor_bytes(entry.type, entry.n)
+        off = entry.offset + first_row * row_bytes
+        view = self.mf.data[off: off + n_rows * row_bytes]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t = torch.from_numpy(view)
+        self.bytes += t.numel()
+        return t.to(self.device, non_blocking=False)
+
+    def f32(self, entry) -> torch.Tensor:
+        x = self.mf.tensor_f32(entry)
+        self.bytes += x.nbytes
+        return torch.from_numpy(np.ascontiguousarray(x)).to(self.device)
+
+
+def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="cuda") -> DeviceWeights:
+    h = mf.header
+    if h.weight_type != quants.F_Q40:
+        raise NotImplementedError("the CUDA engine currently runs q40 weight files (as the reference's GPU/CPU fast path)")
+    H = host()
+    if h.n_heads % n_ranks or h.n_kv_heads % n_ranks or h.ff_dim % n_ranks or h.vocab_size % n_ranks:
+        raise ValueError("nHeads, nKvHeads, ffDim and vocabSize must be divisible by the number of ranks")
+    hd = h.head_dim
+    nh, nkv = h.n_heads // n_ranks, h.n_kv_heads // n_ranks
+    q0, kv0, ff0, v0 = nh * hd, nkv * hd, h.ff_dim // n_ranks, h.vocab_size // n_ranks
+    if (q0 % 32) or (ff0 % 32):
+        raise ValueError("column slices must cover whole 32-element quant blocks")
+    neox = h.rope_type == ROPE_FALCON
+    up = _Uploader(mf, device)
+    dim = h.dim
+
+    def row_sliced(name, layer, expert, dst: DeviceQ40, rows_local, dst_stride=1, dst_off=0, head_dim=0):
+        e = mf.entry(name, layer, expert)
+        raw = up.rows(e, rank * rows_local, rows_local)
+        repack_q40(raw, rows_local, e.n, dst, dst_row_stride=dst_stride, dst_row_offset=dst_off, head_dim=head_dim)
+
+    def col_sliced(name, layer, expert, dst: DeviceQ40, cols_local, dst_off=0):
+        e = mf.entry(name, layer, expert)
+        raw = up.rows(e, 0, e.d)
+        repack_q40(raw, e.d, cols_local, dst, src_row_pitch=quants.tensor_bytes(e.type, e.n),
+                   src_col_byte_offset=quants.tensor_bytes(e.type, rank * cols_local), dst_row_offset=dst_off)
+
+    W = DeviceWeights(header=h, rank=rank, n_ranks=n_ranks, n_heads=nh, n_kv_heads=nkv, ff_dim=ff0, vocab=v0,
+                      embedding=up.f32(mf.entry("embedding")), final_norm=up.f32(mf.entry("final_norm")),
+                      wcls=DeviceQ40.empty(v0, dim, device),
+                      rope=torch.from_numpy(np.asarray(H.build_rope_table(h, h.seq_len))).to(device))
+    row_sliced("final_matmul_logits", 0, 0, W.wcls, v0)
+    perm = torch.from_numpy(_interleave_perm(hd)).to(device) if neox else None
+    n_exp = max(h.n_experts, 1)
+    for l in range(h.n_layers):
+        qkv = DeviceQ40.empty(q0 + 2 * kv0, dim, device)
+        row_sliced("block_matmul_q", l, 0, qkv, q0, head_dim=hd if neox else 0)
+        row_sliced("block_matmul_k", l, 0, qkv, kv0, dst_off=q0, head_dim=hd if neox else 0)
+        row_sliced("block_matmul_v", l, 0, qkv, kv0, dst_off=q0 + kv0)
+        wo = DeviceQ40.empty(dim, q0, device)
+        col_sliced("block_matmul_wo", l, 0, wo, q0)
+        w13 = DeviceQ40.empty(2 * ff0, dim, device, lead=n_exp)
+        w2 = DeviceQ40.empty(dim, ff0, device, lead=n_exp)
+        for e in range(n_exp):
+            row_sliced("block_matmul_w1", l, e, w13, ff0, dst_stride=2, dst_off=e * 2 * ff0)
+            row_sliced("block_matmul_w3", l, e, w13, ff0, dst_stride=2, dst_off=e * 2 * ff0 + 1)
+            col_sliced("block_matmul_w2", l, e, w2, ff0, dst_off=e * dim)
+        L = LayerWeights(qkv=qkv, wo=wo, w13=w13, w2=w2, norm0=up.f32(mf.entry("block_norm_0", l)),
+                         norm1=up.f32(mf.entry("block_norm_1", l)))
+        if h.qk_norm:
+            qn, kn = up.f32(mf.entry("block_norm_q", l)), up.f32(mf.entry("block_norm_k", l))
+            L.q_norm = qn[perm].contiguous() if neox else qn
+            L.k_norm = kn[perm].contiguous() if neox else kn
+        if h.n_experts > 0:
+            L.moe_gate = up.f32(mf.entry("block_moe_gate", l))
+        W.layers.append(L)
+    torch.cuda.synchronize(device)
+    W.bytes_uploaded = up.bytes
+    return W

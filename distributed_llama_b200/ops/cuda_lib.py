@@ -1,0 +1,78 @@
+"""ctypes binding of the sm_100a kernel/runtime library (csrc/cuda -> distributed_llama_b200/_cuda.so).
+
+The library is torch-free: tensors cross the boundary as raw device pointers + the current CUDA stream handle.
+If the library is missing on a machine with a GPU we build it; failures are loud (no eager fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+from .. import _build
+
+_lib: Optional[C.CDLL] = None
+
+u32, u64, i32, f32, vp = C.c_uint32, C.c_uint64, C.c_int, C.c_float, C.c_void_p
+
+
+class EngineConfig(C.Structure):
+    _fields_ = [(n, u32) for n in ("dim", "nLayers", "nHeads", "nKvHeads", "headDim", "ffDim", "vocab", "seqLen",
+                                   "nExperts", "nActiveExperts", "maxBatch", "nSplits", "rank", "nRanks", "numSms")] + \
+               [("eps", f32), ("usePdl", u32)]
+
+
+class LayerPtrs(C.Structure):
+    _fields_ = [(n, vp) for n in ("qkvQs", "qkvSc", "woQs", "woSc", "w13Qs", "w13Sc", "w2Qs", "w2Sc",
+                                  "norm0", "norm1", "qNorm", "kNorm", "moeGate", "kCache", "vCache")]
+
+
+class GlobalPtrs(C.Structure):
+    _fields_ = [("embedding", vp), ("finalNorm", vp), ("wclsQs", vp), ("wclsSc", vp), ("rope", vp), ("vocabFull", u32),
+                ("tokens", vp), ("pos", vp), ("x", vp), ("qkv", vp), ("z", vp), ("h", vp), ("logits", vp),
+                ("attnPartial", vp), ("attnCounters", vp), ("history", vp), ("expertIdx", vp), ("expertWeight", vp)]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build_cuda()
+    L = C.CDLL(str(path))
+    L.dl_repack_q40.argtypes = [vp, u64, u64, u32, u32, vp, vp, u32, u32, u32, vp]
+    L.dl_repack_q40.restype = i32
+    L.dl_dequant_device_q40.argtypes = [vp, vp, u32, u32, vp, vp]
+    L.dl_dequant_device_q40.restype = i32
+    L.dl_gemv_q40.argtypes = [i32, i32, i32, vp, vp, u32, u32, vp, u32, vp, f32, vp, u32, i32, vp, i32]
+    L.dl_gemv_q40.restype = i32
+    L.dl_engine_create.argtypes = [C.POINTER(EngineConfig)]
+    L.dl_engine_create.restype = vp
+    L.dl_engine_destroy.argtypes = [vp]
+    L.dl_engine_destroy.restype = None
+    L.dl_engine_set_layer.argtypes = [vp, u32, C.POINTER(LayerPtrs)]
+    L.dl_engine_set_layer.restype = i32
+    L.dl_engine_set_globals.argtypes = [vp, C.POINTER(GlobalPtrs)]
+    L.dl_engine_set_globals.restype = i32
+    L.dl_engine_num_sms.argtypes = [vp]
+    L.dl_engine_num_sms.restype = u32
+    L.dl_engine_forward.argtypes = [vp, i32, i32, i32, vp]
+    L.dl_engine_forward.restype = i32
+    L.dl_engine_capture_decode.argtypes = [vp]
+    L.dl_engine_capture_decode.restype = i32
+    L.dl_engine_decode_graph.argtypes = [vp, i32, vp]
+    L.dl_engine_decode_graph.restype = i32
+    _lib = L
+    return L
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise RuntimeError(f"{what} failed with code {code}")
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+PRO_RMSNORM, PRO_PLAIN = 0, 1
+EPI_STORE, EPI_RESIDUAL, EPI_SWIGLU = 0, 1, 2

@@ -1,0 +1,148 @@
+"""Python handle of the native per-rank engine (csrc/cuda/engine.cu).
+
+Owns the device tensors (weights, KV cache, activation buffers), hands their pointers to the C++ engine and exposes
+the three calls the apps need: `prefill(tokens, pos)`, `step(token, pos)` -> logits, and the device-resident greedy
+decode loop `decode_greedy(n)` that replays the captured CUDA graph.
+Plays the role of the reference's RootLlmInference (src/app.cpp:168-208): setBatchSize/setPosition/setToken/forward.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ..models.loader import DeviceWeights
+from ..ops import cuda_lib as cl
+
+
+def _p(t: Optional[torch.Tensor]):
+    return t.data_ptr() if t is not None else None
+
+
+class Engine:
+    def __init__(self, weights: DeviceWeights, max_batch: int = 8, n_splits: int = 0, use_pdl: bool = True,
+                 seq_len: Optional[int] = None):
+        self.w = w = weights
+        h = w.header
+        dev = w.embedding.device
+        self.device = dev
+        self.seq_len = seq_len or h.seq_len
+        self.max_batch = max_batch
+        props = torch.cuda.get_device_properties(dev)
+        self.num_sms = props.multi_processor_count
+        if n_splits <= 0:
+            n_splits = max(1, min(32, (2 * self.num_sms) // max(1, w.n_heads)))
+        self.n_splits = n_splits
+        hd = h.head_dim
+        q_dim, kv_dim = w.n_heads * hd, w.n_kv_heads * hd
+        self.qkv_dim = q_dim + 2 * kv_dim
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.tokens = torch.zeros(max_batch, dtype=torch.int32, device=dev)
+        self.pos = torch.zeros(max_batch, dtype=torch.int32, device=dev)
+        self.x = torch.zeros(max_batch, h.dim, **f32)
+        self.qkv = torch.zeros(max_batch, self.qkv_dim, **f32)
+        self.z = torch.zeros(max_batch, q_dim, **f32)
+        self.h = torch.zeros(max_batch, w.ff_dim, **f32)
+        self.logits = torch.zeros(max_batch, w.vocab, **f32)
+        self.attn_partial = torch.zeros(max_batch * w.n_heads * n_splits * (hd + 2), **f32)
+        self.attn_counters = torch.zeros(max_batch * w.n_heads, dtype=torch.int32, device=dev)
+        self.history = torch.zeros(self.seq_len + 1, dtype=torch.int32, device=dev)
+        self.k_cache = [torch.zeros(w.n_kv_heads, self.seq_len, hd, dtype=torch.bfloat16, device=dev) for _ in range(h.n_layers)]
+        self.v_cache = [torch.zeros(w.n_kv_heads, self.seq_len, hd, dtype=torch.bfloat16, device=dev) for _ in range(h.n_layers)]
+        self.expert_idx = torch.zeros(max_batch * max(1, h.n_active_experts), dtype=torch.int32, device=dev)
+        self.expert_weight = torch.zeros(max_batch * max(1, h.n_active_experts), **f32)
+
+        cfg = cl.EngineConfig(dim=h.dim, nLayers=h.n_layers, nHeads=w.n_heads, nKvHeads=w.n_kv_heads, headDim=hd,
+                              ffDim=w.ff_dim, vocab=w.vocab, seqLen=self.seq_len, nExperts=h.n_experts,
+                              nActiveExperts=h.n_active_experts, maxBatch=max_batch, nSplits=n_splits, rank=w.rank,
+                              nRanks=w.n_ranks, numSms=self.num_sms, eps=h.norm_epsilon, usePdl=1 if use_pdl else 0)
+        self._lib = cl.lib()
+        self._h = self._lib.dl_engine_create(C.byref(cfg))
+        for l, L in enumerate(w.layers):
+            lp = cl.LayerPtrs(qkvQs=_p(L.qkv.qs), qkvSc=_p(L.qkv.scales), woQs=_p(L.wo.qs), woSc=_p(L.wo.scales),
+                              w13Qs=_p(L.w13.qs), w13Sc=_p(L.w13.scales), w2Qs=_p(L.w2.qs), w2Sc=_p(L.w2.scales),
+                              norm0=_p(L.norm0), norm1=_p(L.norm1), qNorm=_p(L.q_norm), kNorm=_p(L.k_norm),
+                              moeGate=_p(L.moe_gate), kCache=_p(self.k_cache[l]), vCache=_p(self.v_cache[l]))
+            cl.check(self._lib.dl_engine_set_layer(self._h, l, C.byref(lp)), "engine_set_layer")
+        gp = cl.GlobalPtrs(embedding=_p(w.embedding), finalNorm=_p(w.final_norm), wclsQs=_p(w.wcls.qs),
+                           wclsSc=_p(w.wcls.scales), rope=_p(w.rope), vocabFull=h.vocab_size, tokens=_p(self.tokens),
+                           pos=_p(self.pos), x=_p(self.x), qkv=_p(self.qkv), z=_p(self.z), h=_p(self.h),
+                           logits=_p(self.logits), attnPartial=_p(self.attn_partial), attnCounters=_p(self.attn_counters),
+                           history=_p(self.history), expertIdx=_p(self.expert_idx), expertWeight=_p(self.expert_weight))
+        cl.check(self._lib.dl_engine_set_globals(self._h, C.byref(gp)), "engine_set_globals")
+        self._graph_ready = False
+        self._stage_tok = torch.zeros(max_batch, dtype=torch.int32).pin_memory()
+        self._stage_pos = torch.zeros(max_batch, dtype=torch.int32).pin_memory()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.dl_engine_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- low level --
+    def _set_inputs(self, tokens: Sequence[int], start_pos: int):
+        n = len(tokens)
+        self._stage_tok[:n] = torch.as_tensor(list(tokens), dtype=torch.int32)
+        self._stage_pos[:n] = torch.arange(start_pos, start_pos + n, dtype=torch.int32)
+        self.tokens[:n].copy_(self._stage_tok[:n], non_blocking=True)
+        self.pos[:n].copy_(self._stage_pos[:n], non_blocking=True)
+
+    def forward_batch(self, tokens: Sequence[int], start_pos: int, logits_mode: int = 1, greedy_advance: bool = False):
+        """Runs one forward over len(tokens) in {1,2,4,8} tokens at consecutive positions."""
+        n = len(tokens)
+        if start_pos + n > self.seq_len:
+            raise ValueError("position beyond the context length")
+        self._set_inputs(tokens, start_pos)
+        cl.check(self._lib.dl_engine_forward(self._h, n, logits_mode, 1 if greedy_advance else 0, cl.stream_ptr()), "engine_forward")
+
+    def prefill(self, tokens: Sequence[int], start_pos: int = 0, want_logits: bool = True) -> Optional[torch.Tensor]:
+        """Feeds a prompt chunk by chunk; returns the logits row of the last token (device tensor view)."""
+        tokens = list(tokens)
+        i = 0
+        while i < len(tokens):
+            rem = len(tokens) - i
+            n = 1
+            while n * 2 <= min(rem, self.max_batch):
+                n *= 2
+            last = i + n == len(tokens)
+            self.forward_batch(tokens[i:i + n], start_pos + i, logits_mode=1 if (last and want_logits) else 0)
+            i += n
+        return self.logits[0] if want_logits else None
+
+    def step(self, token: int, pos: int) -> torch.Tensor:
+        self.forward_batch([token], pos, logits_mode=1)
+        return self.logits[0]
+
+    def logits_all(self, tokens: Sequence[int], start_pos: int) -> torch.Tensor:
+        """Logits for every token of a (<= max_batch, power of two) batch — used by perplexity and tests."""
+        self.forward_batch(tokens, start_pos, logits_mode=2)
+        return self.logits[: len(tokens)]
+
+    # -- device-resident greedy decoding --
+    def capture_decode(self):
+        cl.check(self._lib.dl_engine_capture_decode(self._h), "engine_capture_decode")
+        self._graph_ready = True
+
+    def decode_greedy(self, first_token: int, start_pos: int, n_steps: int, use_graph: bool = True) -> List[int]:
+        """Generates n_steps tokens greedily: step i consumes the token at position start_pos+i and emits the next.
+        The loop runs entirely on the device (token + position live in device memory)."""
+        if start_pos + n_steps > self.seq_len:
+            raise ValueError("decode would run past the context length")
+        self._set_inputs([first_token], start_pos)
+        if use_graph:
+            if not self._graph_ready:
+                # warm-up run configures kernel attributes outside of capture
+                cl.check(self._lib.dl_engine_forward(self._h, 1, 1, 0, cl.stream_ptr()), "engine_forward")
+                torch.cuda.current_stream().synchronize()
+                self.capture_decode()
+            cl.check(self._lib.dl_engine_decode_graph(self._h, n_steps, cl.stream_ptr()), "engine_decode_graph")
+        else:
+            for _ in range(n_steps):
+                cl.check(self._lib.dl_engine_forward(self._h, 1, 1, 1, cl.stream_ptr()), "engine_forward")
+        out = self.history[start_pos + 1: start_pos + 1 + n_steps].cpu()
+        return out.tolist()
