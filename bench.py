@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Headline benchmark: batch-1 decode tokens/s (+ prefill TTFT) of Llama-3.1-8B q40, tensor-parallel over N B200s.
+
+    python bench.py --gpus 1 --steps 64 --warmup 8
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29501 \
+        bench.py --gpus 4 --steps 64 --warmup 8
+    python bench.py --impl reference --gpus 1 --steps 32 --warmup 3     # unmodified reference (CPU build, TCP loopback)
+
+Metric definition follows the reference's own benchmark mode (`dllama inference`, src/dllama.cpp:76-115): one "step"
+is one generated token of a single sequence (forward of 1 token through all layers + sampling); `value` is the
+whole-job tokens/s. The model is random-init in the real `.m` layout (no network for checkpoints); weights (4.5 GB) are
+far larger than L2 (126 MB) so every step streams them from HBM — no L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# Published numbers of the reference (report/report.pdf, Llama 2 7B q40 on Raspberry Pi 4B, ms per token by device count).
+PUBLISHED_MS_PER_TOKEN = {1: 1312.50, 2: 793.69, 4: 494.00, 8: 588.19}
+
+CACHE_DIR = os.environ.get("DLLAMA_BENCH_DIR", "/tmp/dllama_bench")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def ensure_model(name: str, max_seq_len_hint: int = 0):
+    """Synthetic model + tokenizer in the real file formats (cached per box)."""
+    from distributed_llama_b200.models.config import get_config
+    from distributed_llama_b200.models.synthetic import write_synthetic_model, write_synthetic_tokenizer
+
+    os.makedirs(CACHE_DIR, exist_ok=True)
+    cfg = get_config(name)
+    m = os.path.join(CACHE_DIR, f"dllama_model_{name}_q40.m")
+    t = os.path.join(CACHE_DIR, f"dllama_tokenizer_{name}.t")
+    if not os.path.exists(m):
+        t0 = time.time()
+        size = write_synthetic_model(m, cfg, seed=20240607)
+        log(f"[bench] wrote {m} ({size / 1e9:.2f} GB) in {time.time() - t0:.1f}s")
+    if not os.path.exists(t):
+        write_synthetic_tokenizer(t, cfg.vocab_size, style="chatml" if name.startswith("qwen") else "llama3")
+    return m, t
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        try:
+            self.proc = subprocess.Popen([exe, f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        clocks, max_clock, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                clocks.append(float(parts[0]))
+                max_clock = max(max_clock, float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        clocks.sort()
+        # "under load" = upper half of the samples (the sampler also sees idle gaps before/after)
+        load = clocks[len(clocks) // 2:] if clocks else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": max_clock or None, "reasons": sorted(reasons), "samples": len(clocks)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("for --gpus N>1 launch with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        from distributed_llama_b200.parallel.comm import Communicator
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        comm = Communicator()
+
+    if rank == 0:
+        model_path, tok_path = ensure_model(args.model)
+    if world > 1:
+        dist.barrier()
+    model_path, tok_path = ensure_model(args.model)
+
+    from distributed_llama_b200.api import InferenceSession
+
+    t0 = time.time()
+    sess = InferenceSession(model_path, tok_path, max_seq_len=args.max_seq_len, temperature=0.0, comm=comm)
+    eng = sess.engine
+    log(f"[bench] rank {rank}: weights on device in {time.time() - t0:.1f}s ({sess.weights.bytes_uploaded / 1e9:.2f} GB uploaded)")
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    prompt = [(7 * i + 3) % 1000 + 1 for i in range(args.prompt_len)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- prefill (TTFT): prompt evaluated + first token sampled ----
+    ttft = []
+    for it in range(3):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        eng.prefill(prompt[:-1], 0, want_logits=False)
+        eng.decode_greedy(prompt[-1], len(prompt) - 1, 1)
+        e.record()
+        torch.cuda.synchronize()
+        ttft.append(max_over_ranks(s.elapsed_time(e)))
+    ttft_ms = min(ttft[1:])
+
+    # ---- decode: device-timed, graph-replayed steps, no host involvement inside the region ----
+    pos0 = len(prompt) - 1
+    eng.decode_greedy(prompt[-1], pos0, warmup)            # warm-up (also captures the graph)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    toks = eng.decode_greedy(prompt[-1], pos0, steps)
+    e.record()
+    barrier()
+    dev_ms = max_over_ranks(s.elapsed_time(e))
+    # ---- end-to-end through the public API: per step H2D(token,pos) from pinned memory + D2H(token) ----
+    sess.pos = pos0
+    tok = prompt[-1]
+    for _ in range(warmup):
+        tok = sess.next_token(tok)
+    sess.pos = pos0
+    tok = prompt[-1]
+    barrier()
+    t_start = time.perf_counter()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    e2e_tokens = []
+    for _ in range(steps):
+        tok = sess.next_token(tok)
+        e2e_tokens.append(tok)
+    e2.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(s2.elapsed_time(e2), (time.perf_counter() - t_start) * 1e3 if world == 1 else 0.0))
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        ms_per_step = dev_ms / steps
+        value = 1000.0 / ms_per_step
+        base = 1000.0 / PUBLISHED_MS_PER_TOKEN.get(args.gpus, PUBLISHED_MS_PER_TOKEN[1])
+        h = sess.header
+        weight_bytes = sum(L.qkv.qs.numel() * 4 + L.qkv.scales.numel() * 2 + L.wo.qs.numel() * 4 + L.wo.scales.numel() * 2 +
+                           L.w13.qs.numel() * 4 + L.w13.scales.numel() * 2 + L.w2.qs.numel() * 4 + L.w2.scales.numel() * 2
+                           for L in sess.weights.layers) + sess.weights.wcls.qs.numel() * 4 + sess.weights.wcls.scales.numel() * 2
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        out = {
+            "metric": "decode tokens/sec (batch-1 sequence, greedy) + prefill TTFT, Llama-3.1-8B q40" if args.model == "llama-3.1-8b"
+                      else f"decode tokens/sec + prefill TTFT, {args.model} q40",
+            "value": round(value, 2), "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": round(value / base, 2), "dtype": "q40 weights, q80 activations (int8 dp4a), bf16 KV, f32 accum",
+            "data": "synthetic (random-init weights in .m layout, synthetic prompt)",
+            "config": {"model": args.model, "global_batch": 1, "seq_len": args.prompt_len + steps, "prompt_len": args.prompt_len,
+                       "parallelism": f"tp{args.gpus}", "l2_policy": "weights per step (%.2f GB/GPU) >> 126 MB L2, no flush needed" % (weight_bytes / 1e9),
+                       "baseline_ref": "reference published Llama-2-7B q40 ms/token on %d x RPi 4B (report.pdf)" % args.gpus},
+            "ttft_ms": round(ttft_ms, 3), "prefill_tokens_per_s": round(args.prompt_len / ttft_ms * 1e3, 1),
+            "e2e": {"value": round(steps / e2e_ms * 1e3, 2), "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": eng.launches_per_decode_step * steps,
+            "hbm_roofline": {"weight_bytes_per_step_per_gpu": weight_bytes, "achieved_gbs": round(weight_bytes / ms_per_step / 1e6, 1),
+                             "frac_of_measured_hbm": round(weight_bytes / ms_per_step / 1e6 / hbm, 3)},
+            "clocks": clocks, "tokens_agree": e2e_tokens == toks, "impl": "ours",
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------
+def ref_binary():
+    src = os.path.join(ROOT, "baseline", "_ref", "distributed-llama")
+    exe = os.path.join(src, "dllama")
+    if not os.path.isdir(src):
+        if os.path.isdir("/root/reference"):
+            os.makedirs(os.path.dirname(src), exist_ok=True)
+            shutil.copytree("/root/reference", src)
+            subprocess.run(["chmod", "-R", "u+w", src])
+        else:
+            return None, "reference sources not present under baseline/_ref"
+    # always (re)build on the box we run on: the reference Makefile uses -march=native
+    stamp = os.path.join(src, ".built_on")
+    host_id = open("/proc/cpuinfo").read().split("model name")[1].split("\n")[0] if os.path.exists("/proc/cpuinfo") else "?"
+    if not os.path.exists(exe) or not os.path.exists(stamp) or open(stamp).read() != host_id:
+        subprocess.run(["make", "clean"], cwd=src, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        r = subprocess.run(["make", "dllama", f"-j{os.cpu_count() or 4}"], cwd=src, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0 or not os.path.exists(exe):
+            return None, "reference build failed: " + r.stdout[-300:].replace("\n", " ")
+        open(stamp, "w").write(host_id)
+    return exe, None
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        # ranks other than 0 only exist because the driver launches both arms the same way
+        try:
+            import torch.distributed as dist
+            dist.init_process_group("gloo")
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
+        return
+
+    def finish(payload):
+        print(json.dumps(payload), flush=True)
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            try:
+                import torch.distributed as dist
+                dist.init_process_group("gloo")
+                dist.barrier()
+                dist.destroy_process_group()
+            except Exception:
+                pass
+
+    exe, err = ref_binary()
+    if exe is None:
+        return finish({"impl": "reference", "unavailable": err})
+    model_path, tok_path = ensure_model(args.model)
+    n = args.gpus
+    cores = os.cpu_count() or 8
+    threads = max(1, min(64, cores // n))
+    # power-of-two thread count keeps the reference's work split even
+    threads = 1 << (threads.bit_length() - 1)
+    workers, ports = [], []
+    try:
+        for w in range(n - 1):
+            port = 9999 - w
+            ports.append(port)
+            workers.append(subprocess.Popen([exe, "worker", "--port", str(port), "--nthreads", str(threads)],
+                                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        if workers:
+            time.sleep(2.0)
+        prompt = " ".join(["hello"] * max(1, args.prompt_len - 1))
+        total_steps = args.prompt_len + args.steps + max(args.warmup, 3) + 8
+        cmd = [exe, "inference", "--model", model_path, "--tokenizer", tok_path, "--buffer-float-type", "q80",
+               "--prompt", prompt, "--steps", str(total_steps), "--nthreads", str(threads), "--temperature", "0",
+               "--max-seq-len", str(max(args.max_seq_len, total_steps + 8))]
+        if ports:
+            cmd += ["--workers"] + [f"127.0.0.1:{p}" for p in ports]
+        t0 = time.time()
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=args.ref_timeout)
+        wall = time.time() - t0
+        text = r.stdout
+        pred = [int(m.group(1)) + int(m.group(2)) for m in re.finditer(r"Pred\s*(\d+) ms Sync\s*(\d+) ms", text)]
+        evals = [(int(m.group(1)) + int(m.group(2)), int(m.group(3))) for m in re.finditer(r"Eval\s*(\d+) ms Sync\s*(\d+) ms.*\((\d+) tokens\)", text)]
+        m_pred = re.search(r"Prediction\s*\n\s*nTokens: (\d+)\s*\n\s*tokens/s: ([\d.]+) \(([\d.]+) ms/tok\)", text)
+        if r.returncode != 0 or not m_pred:
+            return finish({"impl": "reference", "unavailable": "reference run failed: " + text[-300:].replace("\n", " ")})
+        warm = max(args.warmup, 3)
+        timed = pred[warm: warm + args.steps] if len(pred) >= warm + args.steps else pred[warm:]
+        ms_per_step = sum(timed) / max(1, len(timed)) if timed else float(m_pred.group(3))
+        if ms_per_step <= 0:     # ms granularity of the reference's printout; fall back to its own summary
+            ms_per_step = float(m_pred.group(3))
+        value = 1000.0 / ms_per_step
+        eval_ms = sum(e[0] for e in evals)
+        base = 1000.0 / PUBLISHED_MS_PER_TOKEN.get(n, PUBLISHED_MS_PER_TOKEN[1])
+        finish({"metric": "decode tokens/sec (batch-1 sequence, greedy) + prefill TTFT, Llama-3.1-8B q40" if args.model == "llama-3.1-8b"
+                          else f"decode tokens/sec + prefill TTFT, {args.model} q40",
+                "value": round(value, 3), "unit": "tokens/s", "n_gpus": n, "steps": len(timed) or int(m_pred.group(1)), "warmup": warm,
+                "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / base, 2),
+                "dtype": "q40 weights, q80 activations (reference CPU build, AVX)", "data": "synthetic (same .m/.t files)",
+                "config": {"model": args.model, "global_batch": 1, "prompt_len": args.prompt_len, "parallelism": f"tp{n} (root + {n - 1} TCP-loopback workers)",
+                           "nthreads_per_node": threads, "note": "the reference has no CUDA path; its stock build runs on the host CPUs"},
+                "ttft_ms": eval_ms, "impl": "reference", "reference_summary_tokens_per_s": float(m_pred.group(2)), "wall_s": round(wall, 1)})
+    except subprocess.TimeoutExpired:
+        finish({"impl": "reference", "unavailable": "reference run timed out"})
+    finally:
+        for p in workers:
+            try:
+                p.kill()
+            except Exception:
+                pass
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="llama-3.1-8b")
+    ap.add_argument("--prompt-len", type=int, default=64)
+    ap.add_argument("--max-seq-len", type=int, default=2048)
+    ap.add_argument("--ref-timeout", type=int, default=1500)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -84,8 +84,8 @@ PRESETS: Dict[str, ModelConfig] = {
                                  head_dim=128, n_experts=128, n_active_experts=8, moe_hidden_dim=768,
                                  rope_theta=1000000, norm_epsilon=6),
     # test-sized
-    "tiny-llama": ModelConfig("tiny-llama", ARCH_LLAMA, 256, 512, 2, 8, 4, 512, 256, rope_theta=10000),
-    "tiny-llama31": _llama3("tiny-llama31", 256, 512, 2, 8, 4, seq=512, vocab=512),
+    "tiny-llama": ModelConfig("tiny-llama", ARCH_LLAMA, 256, 512, 2, 4, 2, 512, 256, rope_theta=10000),
+    "tiny-llama31": _llama3("tiny-llama31", 512, 1024, 3, 8, 4, seq=512, vocab=512),
     "tiny-qwen3": ModelConfig("tiny-qwen3", ARCH_QWEN3, 256, 512, 2, 4, 2, 512, 256, head_dim=128,
                               rope_theta=1000000, norm_epsilon=6),
     "tiny-qwen3-moe": ModelConfig("tiny-qwen3-moe", ARCH_QWEN3_MOE, 256, 512, 2, 4, 2, 512, 256, head_dim=128,

@@ -124,6 +124,23 @@ class Engine:
         return self.logits[: len(tokens)]
 
     # -- device-resident greedy decoding --
+    def run_decode_step(self, use_graph: bool = True):
+        """One greedy step on whatever (token, pos) currently sit in device memory; result lands in tokens[0]."""
+        if use_graph:
+            if not self._graph_ready:
+                saved = (self.tokens.clone(), self.pos.clone())
+                cl.check(self._lib.dl_engine_forward(self._h, 1, 1, 0, cl.stream_ptr()), "engine_forward")
+                torch.cuda.current_stream().synchronize()
+                self.capture_decode()
+                self.tokens.copy_(saved[0]); self.pos.copy_(saved[1])
+            cl.check(self._lib.dl_engine_decode_graph(self._h, 1, cl.stream_ptr()), "engine_decode_graph")
+        else:
+            cl.check(self._lib.dl_engine_forward(self._h, 1, 1, 1, cl.stream_ptr()), "engine_forward")
+
+    @property
+    def launches_per_decode_step(self) -> int:
+        return self.w.header.n_layers * 6 + 3
+
     def capture_decode(self):
         cl.check(self._lib.dl_engine_capture_decode(self._h), "engine_capture_decode")
         self._graph_ready = True

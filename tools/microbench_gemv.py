@@ -1,6 +1,9 @@
 """GEMV microbenchmark at the Llama-3.1-8B decode shapes: achieved HBM bandwidth per kernel (CUDA events, L2 flushed)."""
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 import torch
