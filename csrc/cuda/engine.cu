@@ -6,6 +6,7 @@
 // programmatic dependent launch, and the single-token step is captured once into a CUDA graph whose inputs
 // (token id, position) live in device memory so the graph replays without host round trips:
 // the sampling kernel writes the next token and advances the position on the device.
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.h"
@@ -48,6 +49,10 @@ struct GlobalPtrs {
     // MoE scratch
     int *expertIdx;              // [maxBatch][nActive]
     float *expertWeight;         // [maxBatch][nActive]
+    // fused arg-max scratch
+    float *argVal;               // [numSms]
+    int *argIdx;                 // [numSms]
+    unsigned int *argCounter;    // [1]
 };
 
 struct Engine {
@@ -57,6 +62,7 @@ struct Engine {
     cudaGraphExec_t decodeGraph = nullptr;
     cudaStream_t captureStream = nullptr;
     int lastError = 0;
+    bool fusedAttn = true, fusedArgmax = true, useTma = true;   // debugging switches (DL_NO_FUSED_ATTN / DL_NO_FUSED_ARGMAX / DL_NO_TMA)
 };
 
 #define DL_TRY(expr)                    \
@@ -64,6 +70,10 @@ struct Engine {
         const int _r = (expr);          \
         if (_r != 0) return _r;         \
     } while (0)
+
+static int gemvSel(const Engine &e, int pro, int epi, int nb, const GemvArgs &a, int numSms, cudaStream_t stream, bool pdl) {
+    return e.useTma ? gemvQ40Auto(pro, epi, nb, a, numSms, stream, pdl) : gemvQ40(pro, epi, nb, a, numSms, stream, pdl);
+}
 
 // logitsMode: 0 = none (prefill chunk), 1 = logits of the last token in the batch into logits[0], 2 = all tokens
 static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, cudaStream_t stream) {
@@ -79,34 +89,44 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
         // 1. rmsnorm -> q80 -> QKV
         a.qs = (const uint32_t *)L.qkvQs; a.scales = (const __half *)L.qkvSc; a.d = qkvDim; a.n = c.dim;
         a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm0; a.eps = c.eps; a.out = e.g.qkv; a.outStride = qkvDim;
-        DL_TRY(gemvQ40(PRO_RMSNORM_, EPI_STORE_, nb, a, c.numSms, stream, pdl));
-        // 2. qk-norm + rope + kv write
-        RopeKvArgs r{};
-        r.qkv = e.g.qkv; r.qkvStride = qkvDim; r.pos = e.g.pos; r.rope = e.g.rope; r.qNorm = L.qNorm; r.kNorm = L.kNorm;
-        r.eps = c.eps; r.nHeads = c.nHeads; r.nKvHeads = c.nKvHeads; r.headDim = c.headDim; r.seqLen = c.seqLen;
-        r.kCache = (__nv_bfloat16 *)L.kCache; r.vCache = (__nv_bfloat16 *)L.vCache;
-        DL_TRY(launchRopeKv(r, nb, stream, pdl));
-        // 3. attention
-        AttnArgs t{};
-        t.qkv = e.g.qkv; t.qkvStride = qkvDim; t.pos = e.g.pos; t.kCache = r.kCache; t.vCache = r.vCache;
-        t.nHeads = c.nHeads; t.nKvHeads = c.nKvHeads; t.headDim = c.headDim; t.seqLen = c.seqLen; t.nSplits = c.nSplits;
-        t.partial = e.g.attnPartial; t.counters = e.g.attnCounters; t.out = e.g.z; t.outStride = qDim;
-        DL_TRY(launchAttnDecode(t, nb, stream, pdl));
+        DL_TRY(gemvSel(e, PRO_RMSNORM_, EPI_STORE_, nb, a, c.numSms, stream, pdl));
+        if (nb == 1 && e.fusedAttn) {
+            // 2+3. qk-norm + rope + kv append + attention in one launch
+            AttnFusedArgs f{};
+            f.qkv = e.g.qkv; f.pos = e.g.pos; f.rope = e.g.rope; f.qNorm = L.qNorm; f.kNorm = L.kNorm; f.eps = c.eps;
+            f.kCache = (__nv_bfloat16 *)L.kCache; f.vCache = (__nv_bfloat16 *)L.vCache;
+            f.nHeads = c.nHeads; f.nKvHeads = c.nKvHeads; f.headDim = c.headDim; f.seqLen = c.seqLen; f.nSplits = c.nSplits;
+            f.partial = e.g.attnPartial; f.counters = e.g.attnCounters; f.out = e.g.z;
+            DL_TRY(launchAttnFused(f, stream, pdl));
+        } else {
+            // 2. qk-norm + rope + kv write
+            RopeKvArgs r{};
+            r.qkv = e.g.qkv; r.qkvStride = qkvDim; r.pos = e.g.pos; r.rope = e.g.rope; r.qNorm = L.qNorm; r.kNorm = L.kNorm;
+            r.eps = c.eps; r.nHeads = c.nHeads; r.nKvHeads = c.nKvHeads; r.headDim = c.headDim; r.seqLen = c.seqLen;
+            r.kCache = (__nv_bfloat16 *)L.kCache; r.vCache = (__nv_bfloat16 *)L.vCache;
+            DL_TRY(launchRopeKv(r, nb, stream, pdl));
+            // 3. attention
+            AttnArgs t{};
+            t.qkv = e.g.qkv; t.qkvStride = qkvDim; t.pos = e.g.pos; t.kCache = r.kCache; t.vCache = r.vCache;
+            t.nHeads = c.nHeads; t.nKvHeads = c.nKvHeads; t.headDim = c.headDim; t.seqLen = c.seqLen; t.nSplits = c.nSplits;
+            t.partial = e.g.attnPartial; t.counters = e.g.attnCounters; t.out = e.g.z; t.outStride = qDim;
+            DL_TRY(launchAttnDecode(t, nb, stream, pdl));
+        }
         // 4. q80 -> WO, residual add
         a = GemvArgs{};
         a.qs = (const uint32_t *)L.woQs; a.scales = (const __half *)L.woSc; a.d = c.dim; a.n = qDim;
         a.in = e.g.z; a.inStride = qDim; a.out = e.g.x; a.outStride = c.dim;
-        DL_TRY(gemvQ40(PRO_PLAIN_, EPI_RESIDUAL_, nb, a, c.numSms, stream, pdl));
+        DL_TRY(gemvSel(e, PRO_PLAIN_, EPI_RESIDUAL_, nb, a, c.numSms, stream, pdl));
         // 5. rmsnorm -> q80 -> W1|W3 -> silu*up
         a = GemvArgs{};
         a.qs = (const uint32_t *)L.w13Qs; a.scales = (const __half *)L.w13Sc; a.d = 2 * c.ffDim; a.n = c.dim;
         a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm1; a.eps = c.eps; a.out = e.g.h; a.outStride = c.ffDim;
-        DL_TRY(gemvQ40(PRO_RMSNORM_, EPI_SWIGLU_, nb, a, c.numSms, stream, pdl));
+        DL_TRY(gemvSel(e, PRO_RMSNORM_, EPI_SWIGLU_, nb, a, c.numSms, stream, pdl));
         // 6. q80 -> W2, residual add
         a = GemvArgs{};
         a.qs = (const uint32_t *)L.w2Qs; a.scales = (const __half *)L.w2Sc; a.d = c.dim; a.n = c.ffDim;
         a.in = e.g.h; a.inStride = c.ffDim; a.out = e.g.x; a.outStride = c.dim;
-        DL_TRY(gemvQ40(PRO_PLAIN_, EPI_RESIDUAL_, nb, a, c.numSms, stream, pdl));
+        DL_TRY(gemvSel(e, PRO_PLAIN_, EPI_RESIDUAL_, nb, a, c.numSms, stream, pdl));
     }
     if (logitsMode != 0) {
         GemvArgs a{};
@@ -114,13 +134,26 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
         a.normW = e.g.finalNorm; a.eps = c.eps; a.inStride = c.dim; a.outStride = c.vocab; a.out = e.g.logits;
         if (logitsMode == 1) {
             a.in = e.g.x + (size_t)(nb - 1) * c.dim;
-            DL_TRY(gemvQ40(PRO_RMSNORM_, EPI_STORE_, 1, a, c.numSms, stream, pdl));
+            int r = 1;
+            if (greedyAdvance && e.fusedArgmax) {
+                // logits + greedy sampling + position advance in one launch
+                a.argVal = e.g.argVal; a.argIdx = e.g.argIdx; a.argCounter = e.g.argCounter;
+                a.tokenOut = e.g.tokens; a.posInOut = e.g.pos; a.history = e.g.history; a.historyCap = c.seqLen;
+                a.rowOffsetGlobal = 0;
+                r = gemvQ40Tma(PRO_RMSNORM_, EPI_ARGMAX_, 1, a, c.numSms, stream, pdl);
+                if (r < 0) return r;
+            }
+            if (r == 1) {
+                DL_TRY(gemvSel(e, PRO_RMSNORM_, EPI_STORE_, 1, a, c.numSms, stream, pdl));
+                if (greedyAdvance)
+                    DL_TRY(launchArgmaxAdvance(e.g.logits, c.vocab, e.g.tokens, e.g.pos, e.g.history, c.seqLen, stream, pdl));
+            }
         } else {
             a.in = e.g.x;
-            DL_TRY(gemvQ40(PRO_RMSNORM_, EPI_STORE_, nb, a, c.numSms, stream, pdl));
+            DL_TRY(gemvSel(e, PRO_RMSNORM_, EPI_STORE_, nb, a, c.numSms, stream, pdl));
+            if (greedyAdvance)
+                DL_TRY(launchArgmaxAdvance(e.g.logits, c.vocab, e.g.tokens, e.g.pos, e.g.history, c.seqLen, stream, pdl));
         }
-        if (greedyAdvance)
-            DL_TRY(launchArgmaxAdvance(e.g.logits, c.vocab, e.g.tokens, e.g.pos, e.g.history, c.seqLen, stream, pdl));
     }
     return 0;
 }
@@ -133,6 +166,9 @@ DL_EXPORT void *dl_engine_create(const dl::EngineConfig *cfg) {
     Engine *e = new Engine();
     e->cfg = *cfg;
     e->layers.resize(cfg->nLayers);
+    e->fusedAttn = std::getenv("DL_NO_FUSED_ATTN") == nullptr;
+    e->fusedArgmax = std::getenv("DL_NO_FUSED_ARGMAX") == nullptr;
+    e->useTma = std::getenv("DL_NO_TMA") == nullptr;
     if (e->cfg.numSms == 0) {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);

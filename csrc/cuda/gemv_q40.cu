@@ -281,12 +281,14 @@ int gemvQ40(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t strea
 // Standalone entry point (tests / microbenchmarks). Engine code calls dl::gemvQ40 directly.
 DL_EXPORT int dl_gemv_q40(int pro, int epi, int nb, const void *qs, const void *scales, uint32_t d, uint32_t n,
                           const float *in, uint32_t inStride, const float *normW, float eps, float *out,
-                          uint32_t outStride, int numSms, cudaStream_t stream, int pdl) {
+                          uint32_t outStride, int numSms, cudaStream_t stream, int pdl, int impl) {
     dl::GemvArgs a{};
     a.qs = (const uint32_t *)qs;
     a.scales = (const __half *)scales;
     a.d = d; a.n = n;
     a.in = in; a.normW = normW; a.eps = eps;
     a.out = out; a.inStride = inStride; a.outStride = outStride;
-    return dl::gemvQ40(pro, epi, nb, a, numSms, stream, pdl != 0);
+    if (impl == 1) return dl::gemvQ40(pro, epi, nb, a, numSms, stream, pdl != 0);
+    if (impl == 2) return dl::gemvQ40Tma(pro, epi, nb, a, numSms, stream, pdl != 0);
+    return dl::gemvQ40Auto(pro, epi, nb, a, numSms, stream, pdl != 0);
 }

@@ -5,7 +5,7 @@
 namespace dl {
 
 enum { PRO_RMSNORM_ = 0, PRO_PLAIN_ = 1 };
-enum { EPI_STORE_ = 0, EPI_RESIDUAL_ = 1, EPI_SWIGLU_ = 2 };
+enum { EPI_STORE_ = 0, EPI_RESIDUAL_ = 1, EPI_SWIGLU_ = 2, EPI_ARGMAX_ = 3 };
 
 struct GemvArgs {
     const uint32_t *qs;
@@ -21,8 +21,20 @@ struct GemvArgs {
     uint32_t slot, kActive;
     uint64_t expertQsStride, expertScaleStride;
     const float *expertWeight;
+    // EPI_ARGMAX (TMA kernel, nb == 1): logits are stored and the greedy token is selected in the same launch
+    float *argVal;            // [grid] per-CTA best value
+    int *argIdx;              // [grid] per-CTA best index
+    unsigned int *argCounter; // zero-initialised, self-resetting
+    int *tokenOut, *posInOut, *history;
+    uint32_t historyCap;
+    uint32_t rowOffsetGlobal; // added to row indices (vocab slice offset under tensor parallelism)
 };
-int gemvQ40(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl);
+int gemvQ40(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl);      // per-thread loads (fallback)
+int gemvQ40Tma(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl);   // TMA ring; returns 1 if shape unsupported
+inline int gemvQ40Auto(int pro, int epi, int nb, const GemvArgs &a, int numSms, cudaStream_t stream, bool pdl) {
+    const int r = gemvQ40Tma(pro, epi, nb, a, numSms, stream, pdl);
+    return r == 1 ? gemvQ40(pro, epi, nb, a, numSms, stream, pdl) : r;
+}
 
 struct RopeKvArgs {
     float *qkv;
@@ -50,6 +62,21 @@ struct AttnArgs {
     uint32_t outStride;
 };
 int launchAttnDecode(const AttnArgs &a, int nb, cudaStream_t stream, bool pdl);
+
+// Single-token decode attention with QK-norm + RoPE + KV-cache append fused in (no separate rope kernel).
+struct AttnFusedArgs {
+    const float *qkv;        // raw q|k|v row of the token (f32, straight from the QKV GEMV)
+    const int *pos;
+    const float *rope;       // [seqLen][hd/2][2]
+    const float *qNorm, *kNorm;
+    float eps;
+    __nv_bfloat16 *kCache, *vCache;
+    uint32_t nHeads, nKvHeads, headDim, seqLen, nSplits;
+    float *partial;
+    unsigned int *counters;
+    float *out;
+};
+int launchAttnFused(const AttnFusedArgs &a, cudaStream_t stream, bool pdl);
 
 int launchEmbedding(const float *table, const int *tokens, float *x, uint32_t dim, uint32_t xStride, uint32_t vocab, int nb,
                     cudaStream_t stream);

@@ -29,7 +29,8 @@ class LayerPtrs(C.Structure):
 class GlobalPtrs(C.Structure):
     _fields_ = [("embedding", vp), ("finalNorm", vp), ("wclsQs", vp), ("wclsSc", vp), ("rope", vp), ("vocabFull", u32),
                 ("tokens", vp), ("pos", vp), ("x", vp), ("qkv", vp), ("z", vp), ("h", vp), ("logits", vp),
-                ("attnPartial", vp), ("attnCounters", vp), ("history", vp), ("expertIdx", vp), ("expertWeight", vp)]
+                ("attnPartial", vp), ("attnCounters", vp), ("history", vp), ("expertIdx", vp), ("expertWeight", vp),
+                ("argVal", vp), ("argIdx", vp), ("argCounter", vp)]
 
 
 def lib() -> C.CDLL:
@@ -42,7 +43,7 @@ def lib() -> C.CDLL:
     L.dl_repack_q40.restype = i32
     L.dl_dequant_device_q40.argtypes = [vp, vp, u32, u32, vp, vp]
     L.dl_dequant_device_q40.restype = i32
-    L.dl_gemv_q40.argtypes = [i32, i32, i32, vp, vp, u32, u32, vp, u32, vp, f32, vp, u32, i32, vp, i32]
+    L.dl_gemv_q40.argtypes = [i32, i32, i32, vp, vp, u32, u32, vp, u32, vp, f32, vp, u32, i32, vp, i32, i32]
     L.dl_gemv_q40.restype = i32
     L.dl_engine_create.argtypes = [C.POINTER(EngineConfig)]
     L.dl_engine_create.restype = vp

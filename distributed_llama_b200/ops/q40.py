@@ -44,12 +44,12 @@ def repack_q40(raw: torch.Tensor, rows: int, n_cols: int, dst: DeviceQ40, *, src
 
 
 def gemv_q40(w: DeviceQ40, x: torch.Tensor, *, pro: int, epi: int, out: torch.Tensor, norm_w: Optional[torch.Tensor] = None,
-             eps: float = 1e-5, num_sms: int = 0, pdl: bool = False) -> torch.Tensor:
+             eps: float = 1e-5, num_sms: int = 0, pdl: bool = False, impl: str = "auto") -> torch.Tensor:
     """x: f32 [nb, n]; out: f32 [nb, d] (STORE / RESIDUAL in place) or [nb, d/2] (SWIGLU)."""
     nb = x.shape[0]
     if num_sms == 0:
         num_sms = torch.cuda.get_device_properties(x.device).multi_processor_count
     cl.check(cl.lib().dl_gemv_q40(pro, epi, nb, w.qs.data_ptr(), w.scales.data_ptr(), w.d, w.n, x.data_ptr(), x.stride(0),
                                   norm_w.data_ptr() if norm_w is not None else None, eps, out.data_ptr(), out.stride(0),
-                                  num_sms, cl.stream_ptr(), 1 if pdl else 0), "gemv_q40")
+                                  num_sms, cl.stream_ptr(), 1 if pdl else 0, {"auto": 0, "ldg": 1, "tma": 2}[impl]), "gemv_q40")
     return out

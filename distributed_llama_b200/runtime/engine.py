@@ -53,6 +53,9 @@ class Engine:
         self.v_cache = [torch.zeros(w.n_kv_heads, self.seq_len, hd, dtype=torch.bfloat16, device=dev) for _ in range(h.n_layers)]
         self.expert_idx = torch.zeros(max_batch * max(1, h.n_active_experts), dtype=torch.int32, device=dev)
         self.expert_weight = torch.zeros(max_batch * max(1, h.n_active_experts), **f32)
+        self.arg_val = torch.zeros(256, **f32)
+        self.arg_idx = torch.zeros(256, dtype=torch.int32, device=dev)
+        self.arg_counter = torch.zeros(4, dtype=torch.int32, device=dev)
 
         cfg = cl.EngineConfig(dim=h.dim, nLayers=h.n_layers, nHeads=w.n_heads, nKvHeads=w.n_kv_heads, headDim=hd,
                               ffDim=w.ff_dim, vocab=w.vocab, seqLen=self.seq_len, nExperts=h.n_experts,
@@ -70,7 +73,8 @@ class Engine:
                            wclsSc=_p(w.wcls.scales), rope=_p(w.rope), vocabFull=h.vocab_size, tokens=_p(self.tokens),
                            pos=_p(self.pos), x=_p(self.x), qkv=_p(self.qkv), z=_p(self.z), h=_p(self.h),
                            logits=_p(self.logits), attnPartial=_p(self.attn_partial), attnCounters=_p(self.attn_counters),
-                           history=_p(self.history), expertIdx=_p(self.expert_idx), expertWeight=_p(self.expert_weight))
+                           history=_p(self.history), expertIdx=_p(self.expert_idx), expertWeight=_p(self.expert_weight),
+                           argVal=_p(self.arg_val), argIdx=_p(self.arg_idx), argCounter=_p(self.arg_counter))
         cl.check(self._lib.dl_engine_set_globals(self._h, C.byref(gp)), "engine_set_globals")
         self._graph_ready = False
         self._stage_tok = torch.zeros(max_batch, dtype=torch.int32).pin_memory()
@@ -86,11 +90,11 @@ class Engine:
 
     # -- low level --
     def _set_inputs(self, tokens: Sequence[int], start_pos: int):
+        # Pageable source tensors: the copy is staged before the call returns, so back-to-back chunks cannot
+        # overwrite a host buffer that an earlier async copy has not consumed yet.
         n = len(tokens)
-        self._stage_tok[:n] = torch.as_tensor(list(tokens), dtype=torch.int32)
-        self._stage_pos[:n] = torch.arange(start_pos, start_pos + n, dtype=torch.int32)
-        self.tokens[:n].copy_(self._stage_tok[:n], non_blocking=True)
-        self.pos[:n].copy_(self._stage_pos[:n], non_blocking=True)
+        self.tokens[:n].copy_(torch.tensor(list(tokens), dtype=torch.int32))
+        self.pos[:n].copy_(torch.arange(start_pos, start_pos + n, dtype=torch.int32))
 
     def forward_batch(self, tokens: Sequence[int], start_pos: int, logits_mode: int = 1, greedy_advance: bool = False):
         """Runs one forward over len(tokens) in {1,2,4,8} tokens at consecutive positions."""
@@ -139,7 +143,7 @@ class Engine:
 
     @property
     def launches_per_decode_step(self) -> int:
-        return self.w.header.n_layers * 6 + 3
+        return self.w.header.n_layers * 5 + 2   # embedding + 5 fused kernels per layer + logits/arg-max
 
     def capture_decode(self):
         cl.check(self._lib.dl_engine_capture_decode(self._h), "engine_capture_decode")

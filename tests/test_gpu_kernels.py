@@ -60,9 +60,10 @@ def _q80(x):
     return q80_round(x)
 
 
+@pytest.mark.parametrize("impl", ["ldg", "tma"])
 @pytest.mark.parametrize("nb", [1, 2, 4, 8])
-@pytest.mark.parametrize("d,n", [(256, 256), (6144, 4096), (4096, 1792), (1000, 2176), (128, 96 * 8)])
-def test_gemv_rmsnorm_store(nb, d, n):
+@pytest.mark.parametrize("d,n", [(256, 256), (6144, 4096), (4096, 1792), (1000, 2176), (128, 96 * 8), (16032, 4096), (402, 14336)])
+def test_gemv_rmsnorm_store(nb, d, n, impl):
     from distributed_llama_b200 import ops
     raw, wq = _rand_q40(d, n, seed=3)
     w = _device_q40(raw, d, n)
@@ -70,7 +71,7 @@ def test_gemv_rmsnorm_store(nb, d, n):
     x = torch.randn(nb, n, device="cuda") * 2.0
     nw = 1.0 + 0.1 * torch.randn(n, device="cuda")
     out = torch.empty(nb, d, device="cuda")
-    ops.gemv_q40(w, x, pro=ops.PRO_RMSNORM, epi=ops.EPI_STORE, out=out, norm_w=nw, eps=1e-5)
+    ops.gemv_q40(w, x, pro=ops.PRO_RMSNORM, epi=ops.EPI_STORE, out=out, norm_w=nw, eps=1e-5, impl=impl)
     y = nw * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5))
     ref_q = _q80(y) @ torch.from_numpy(wq).cuda().T       # same activation grid as the kernel
     ref_f = y @ torch.from_numpy(wq).cuda().T             # un-quantised activations
@@ -78,8 +79,9 @@ def test_gemv_rmsnorm_store(nb, d, n):
     assert (out - ref_f).abs().max() < 0.08 * ref_f.abs().max() + 0.05
 
 
+@pytest.mark.parametrize("impl", ["ldg", "tma"])
 @pytest.mark.parametrize("nb", [1, 4])
-def test_gemv_residual_and_swiglu(nb):
+def test_gemv_residual_and_swiglu(nb, impl):
     from distributed_llama_b200 import ops
     d, n = 512, 1024
     raw, wq = _rand_q40(d, n, seed=4)
@@ -89,12 +91,12 @@ def test_gemv_residual_and_swiglu(nb):
     z = torch.randn(nb, n, device="cuda")
     x = torch.randn(nb, d, device="cuda")
     x0 = x.clone()
-    ops.gemv_q40(w, z, pro=ops.PRO_PLAIN, epi=ops.EPI_RESIDUAL, out=x)
+    ops.gemv_q40(w, z, pro=ops.PRO_PLAIN, epi=ops.EPI_RESIDUAL, out=x, impl=impl)
     torch.testing.assert_close(x, x0 + _q80(z) @ wt.T, rtol=2e-3, atol=2e-3)
     # swiglu: rows interleaved (gate_i, up_i)
     nw = torch.ones(n, device="cuda")
     hbuf = torch.empty(nb, d // 2, device="cuda")
-    ops.gemv_q40(w, z, pro=ops.PRO_RMSNORM, epi=ops.EPI_SWIGLU, out=hbuf, norm_w=nw, eps=1e-6)
+    ops.gemv_q40(w, z, pro=ops.PRO_RMSNORM, epi=ops.EPI_SWIGLU, out=hbuf, norm_w=nw, eps=1e-6, impl=impl)
     y = _q80(z * torch.rsqrt(z.pow(2).mean(-1, keepdim=True) + 1e-6))
     full = y @ wt.T
     ref = torch.nn.functional.silu(full[:, 0::2]) * full[:, 1::2]

@@ -19,36 +19,39 @@ def rand_dev(d, n):
     return w
 
 
-def bench(name, d, n, pro, epi, nb=1, iters=20):
+def bench(name, d, n, pro, epi, nb=1, iters=20, impl="auto"):
     w = rand_dev(d, n)
     x = torch.randn(nb, n, device="cuda")
     nw = torch.ones(n, device="cuda")
     out = torch.zeros(nb, d if epi != ops.EPI_SWIGLU else d // 2, device="cuda")
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    times = []
+    flush = torch.ones(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    evs = []
+    # queue everything first so the CPU stays ahead of the GPU; a *read* of 512 MB leaves L2 full of clean lines
     for i in range(iters + 3):
-        flush.zero_()
+        _ = flush.view(torch.int64).sum()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        ops.gemv_q40(w, x, pro=pro, epi=epi, out=out, norm_w=nw)
+        ops.gemv_q40(w, x, pro=pro, epi=epi, out=out, norm_w=nw, impl=impl)
         e.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            times.append(s.elapsed_time(e) * 1e3)
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    times = [s.elapsed_time(e) * 1e3 for s, e in evs[3:]]
     us = float(np.median(times))
     byts = d * n // 2 + d * n // 32 * 2
-    return dict(kernel=name, d=d, n=n, nb=nb, us=round(us, 2), gbs=round(byts / us / 1e3, 1))
+    return dict(impl=impl, kernel=name, d=d, n=n, nb=nb, us=round(us, 2), gbs=round(byts / us / 1e3, 1))
 
 
 if __name__ == "__main__":
     peaks = json.load(open("MEASURED_PEAKS.json")) if len(sys.argv) < 2 else {"hbm_gbs": float(sys.argv[1])}
-    rows = [bench("qkv", 6144, 4096, ops.PRO_RMSNORM, ops.EPI_STORE),
-            bench("wo", 4096, 4096, ops.PRO_PLAIN, ops.EPI_RESIDUAL),
-            bench("w13", 28672, 4096, ops.PRO_RMSNORM, ops.EPI_SWIGLU),
-            bench("w2", 4096, 14336, ops.PRO_PLAIN, ops.EPI_RESIDUAL),
-            bench("logits", 128256, 4096, ops.PRO_RMSNORM, ops.EPI_STORE),
-            bench("w13_nb4", 28672, 4096, ops.PRO_RMSNORM, ops.EPI_SWIGLU, nb=4),
-            bench("w13_nb8", 28672, 4096, ops.PRO_RMSNORM, ops.EPI_SWIGLU, nb=8)]
+    rows = []
+    for impl in ("ldg", "tma"):
+        rows += [bench("qkv", 6144, 4096, ops.PRO_RMSNORM, ops.EPI_STORE, impl=impl),
+                 bench("wo", 4096, 4096, ops.PRO_PLAIN, ops.EPI_RESIDUAL, impl=impl),
+                 bench("w13", 28672, 4096, ops.PRO_RMSNORM, ops.EPI_SWIGLU, impl=impl),
+                 bench("w2", 4096, 14336, ops.PRO_PLAIN, ops.EPI_RESIDUAL, impl=impl),
+                 bench("logits", 128256, 4096, ops.PRO_RMSNORM, ops.EPI_STORE, impl=impl),
+                 bench("w13_nb4", 28672, 4096, ops.PRO_RMSNORM, ops.EPI_SWIGLU, nb=4, impl=impl),
+                 bench("w13_nb8", 28672, 4096, ops.PRO_RMSNORM, ops.EPI_SWIGLU, nb=8, impl=impl)]
     for r in rows:
         r["frac_of_measured_hbm"] = round(r["gbs"] / peaks["hbm_gbs"], 3)
         print(json.dumps(r))
