@@ -82,6 +82,17 @@ __device__ __forceinline__ int dp4a(uint32_t a, uint32_t b, int c) {
     return d;
 }
 
+// ---- in-kernel timeline (globaltimer ns) -----------------------------------------------------------------
+// CTA 0 / thread 0 of every kernel stamps: [0] entry, [1] dependency resolved, [2] prologue done, [3] exit.
+__device__ __forceinline__ uint64_t globalTimerNs() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void traceStamp(uint64_t *trace, int which) {
+    if (trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) trace[which] = globalTimerNs();
+}
+
 __device__ __forceinline__ float siluf(float x) { return x / (1.0f + __expf(-x)); }
 
 }  // namespace dl

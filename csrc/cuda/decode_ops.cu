@@ -207,8 +207,10 @@ template <int HD>
 __global__ void __launch_bounds__(128) attnFusedKernel(AttnFusedArgs a) {
     constexpr int DPL = HD / 32;
     static_assert(DPL == 2 || DPL == 4, "head dim must be 64 or 128");
+    traceStamp(a.trace, 0);
     pdlLaunchDependents();
     pdlWait();
+    traceStamp(a.trace, 1);
     __shared__ float sAcc[4][HD];
     __shared__ float sM[4], sL[4];
     __shared__ bool sLast;
@@ -366,6 +368,7 @@ __global__ void __launch_bounds__(128) attnFusedKernel(AttnFusedArgs a) {
     float *outRow = a.out + (size_t)h * HD;
     if (eff == 1) {
         if (threadIdx.x < HD) outRow[threadIdx.x] = num / L;
+        traceStamp(a.trace, 3);
         return;
     }
     float *pOut = a.partial + ((size_t)h * a.nSplits + split) * (HD + 2);

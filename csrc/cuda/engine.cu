@@ -62,6 +62,8 @@ struct Engine {
     cudaGraphExec_t decodeGraph = nullptr;
     cudaStream_t captureStream = nullptr;
     int lastError = 0;
+    uint64_t *trace = nullptr;   // device buffer [maxLaunches][4] of globaltimer stamps (optional)
+    uint32_t traceCap = 0;
     bool fusedAttn = true, fusedArgmax = true, useTma = true;   // debugging switches (DL_NO_FUSED_ATTN / DL_NO_FUSED_ARGMAX / DL_NO_TMA)
 };
 
@@ -81,6 +83,8 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
     const bool pdl = c.usePdl != 0;
     const uint32_t qDim = c.nHeads * c.headDim, kvDim = c.nKvHeads * c.headDim, qkvDim = qDim + 2 * kvDim;
     if (nb < 1 || (uint32_t)nb > c.maxBatch || (nb & (nb - 1))) return -10;
+    uint32_t slot = 0;
+    auto nextTrace = [&]() -> uint64_t * { uint64_t *t = (e.trace && slot < e.traceCap) ? e.trace + (size_t)slot * 4 : nullptr; slot++; return t; };
 
     DL_TRY(launchEmbedding(e.g.embedding, e.g.tokens, e.g.x, c.dim, c.dim, e.g.vocabFull, nb, stream));
     for (uint32_t l = 0; l < c.nLayers; l++) {
@@ -88,7 +92,7 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
         GemvArgs a{};
         // 1. rmsnorm -> q80 -> QKV
         a.qs = (const uint32_t *)L.qkvQs; a.scales = (const __half *)L.qkvSc; a.d = qkvDim; a.n = c.dim;
-        a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm0; a.eps = c.eps; a.out = e.g.qkv; a.outStride = qkvDim;
+        a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm0; a.eps = c.eps; a.out = e.g.qkv; a.outStride = qkvDim; a.trace = nextTrace();
         DL_TRY(gemvSel(e, PRO_RMSNORM_, EPI_STORE_, nb, a, c.numSms, stream, pdl));
         if (nb == 1 && e.fusedAttn) {
             // 2+3. qk-norm + rope + kv append + attention in one launch
@@ -96,7 +100,7 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
             f.qkv = e.g.qkv; f.pos = e.g.pos; f.rope = e.g.rope; f.qNorm = L.qNorm; f.kNorm = L.kNorm; f.eps = c.eps;
             f.kCache = (__nv_bfloat16 *)L.kCache; f.vCache = (__nv_bfloat16 *)L.vCache;
             f.nHeads = c.nHeads; f.nKvHeads = c.nKvHeads; f.headDim = c.headDim; f.seqLen = c.seqLen; f.nSplits = c.nSplits;
-            f.partial = e.g.attnPartial; f.counters = e.g.attnCounters; f.out = e.g.z;
+            f.partial = e.g.attnPartial; f.counters = e.g.attnCounters; f.out = e.g.z; f.trace = nextTrace();
             DL_TRY(launchAttnFused(f, stream, pdl));
         } else {
             // 2. qk-norm + rope + kv write
@@ -115,23 +119,23 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
         // 4. q80 -> WO, residual add
         a = GemvArgs{};
         a.qs = (const uint32_t *)L.woQs; a.scales = (const __half *)L.woSc; a.d = c.dim; a.n = qDim;
-        a.in = e.g.z; a.inStride = qDim; a.out = e.g.x; a.outStride = c.dim;
+        a.in = e.g.z; a.inStride = qDim; a.out = e.g.x; a.outStride = c.dim; a.trace = nextTrace();
         DL_TRY(gemvSel(e, PRO_PLAIN_, EPI_RESIDUAL_, nb, a, c.numSms, stream, pdl));
         // 5. rmsnorm -> q80 -> W1|W3 -> silu*up
         a = GemvArgs{};
         a.qs = (const uint32_t *)L.w13Qs; a.scales = (const __half *)L.w13Sc; a.d = 2 * c.ffDim; a.n = c.dim;
-        a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm1; a.eps = c.eps; a.out = e.g.h; a.outStride = c.ffDim;
+        a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm1; a.eps = c.eps; a.out = e.g.h; a.outStride = c.ffDim; a.trace = nextTrace();
         DL_TRY(gemvSel(e, PRO_RMSNORM_, EPI_SWIGLU_, nb, a, c.numSms, stream, pdl));
         // 6. q80 -> W2, residual add
         a = GemvArgs{};
         a.qs = (const uint32_t *)L.w2Qs; a.scales = (const __half *)L.w2Sc; a.d = c.dim; a.n = c.ffDim;
-        a.in = e.g.h; a.inStride = c.ffDim; a.out = e.g.x; a.outStride = c.dim;
+        a.in = e.g.h; a.inStride = c.ffDim; a.out = e.g.x; a.outStride = c.dim; a.trace = nextTrace();
         DL_TRY(gemvSel(e, PRO_PLAIN_, EPI_RESIDUAL_, nb, a, c.numSms, stream, pdl));
     }
     if (logitsMode != 0) {
         GemvArgs a{};
         a.qs = (const uint32_t *)e.g.wclsQs; a.scales = (const __half *)e.g.wclsSc; a.d = c.vocab; a.n = c.dim;
-        a.normW = e.g.finalNorm; a.eps = c.eps; a.inStride = c.dim; a.outStride = c.vocab; a.out = e.g.logits;
+        a.normW = e.g.finalNorm; a.eps = c.eps; a.inStride = c.dim; a.outStride = c.vocab; a.out = e.g.logits; a.trace = nextTrace();
         if (logitsMode == 1) {
             a.in = e.g.x + (size_t)(nb - 1) * c.dim;
             int r = 1;
@@ -195,6 +199,12 @@ DL_EXPORT int dl_engine_set_layer(void *h, uint32_t layer, const dl::LayerPtrs *
 
 DL_EXPORT int dl_engine_set_globals(void *h, const dl::GlobalPtrs *p) {
     ((Engine *)h)->g = *p;
+    return 0;
+}
+
+DL_EXPORT int dl_engine_set_trace(void *h, uint64_t *buf, uint32_t capLaunches) {
+    ((Engine *)h)->trace = buf;
+    ((Engine *)h)->traceCap = capLaunches;
     return 0;
 }
 

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
     uint64_t *fullBar = reinterpret_cast<uint64_t *>(red + 32);             // [nStages]
     uint64_t *emptyBar = fullBar + kMaxStages;                              // [nStages]
 
+    traceStamp(a.trace, 0);
     pdlLaunchDependents();
     if (tid == 0) {
         for (uint32_t s = 0; s < geo.nStages; s++) {
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
             asm volatile("prefetch.global.L2 [%0];" ::"l"(a.normW + i));
     }
     pdlWait();
+    traceStamp(a.trace, 1);
 
     // ---- prologue: (rmsnorm) + q80 quantisation into the dp4a plane layout ----
     {
@@ -222,6 +224,7 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
         }
     }
     consumerBarrier();
+    traceStamp(a.trace, 2);
 
     // ---- main loop over ring stages ----
     for (uint32_t f = 0; f < nFills; f++) {
@@ -233,8 +236,13 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
         const uint8_t *stage = ring + (size_t)st * geo.stageBytes;
         const uint4 *sq = reinterpret_cast<const uint4 *>(stage);
         const uint16_t *ss = reinterpret_cast<const uint16_t *>(stage + (size_t)SR * rowQsBytes);
+        // steps are dealt round-robin over the 16 warps *across* fills (a stage may hold fewer than 16 steps)
+        const uint32_t stepsPerFullStage = (SR / kRowsPerStep > 0 ? SR / kRowsPerStep : 1) * nseg;
+        const uint32_t firstStep = (warp + kConsumerWarps - (f * stepsPerFullStage) % kConsumerWarps) % kConsumerWarps;
+        // every warp waits (even one without steps in this fill): it keeps all warps within one ring revolution, so no
+        // warp can arrive twice on the same empty-barrier phase
         mbarWait(&fullBar[st], (f / geo.nStages) & 1);
-        for (uint32_t s = warp; s < nSteps; s += kConsumerWarps) {
+        for (uint32_t s = firstStep; s < nSteps; s += kConsumerWarps) {
             const uint32_t g = s / nseg, seg = s - g * nseg;
             const uint32_t blk = seg * 32 + lane;
             const uint32_t rl = g * kRowsPerStep;                  // first row of the group inside the stage
@@ -379,6 +387,7 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
             }
         }
     }
+    traceStamp(a.trace, 3);
 }
 
 template <int PRO, int EPI, int NB>

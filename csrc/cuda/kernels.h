@@ -28,6 +28,7 @@ struct GemvArgs {
     int *tokenOut, *posInOut, *history;
     uint32_t historyCap;
     uint32_t rowOffsetGlobal; // added to row indices (vocab slice offset under tensor parallelism)
+    uint64_t *trace;          // optional 4-slot timeline record for this launch
 };
 int gemvQ40(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl);      // per-thread loads (fallback)
 int gemvQ40Tma(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl);   // TMA ring; returns 1 if shape unsupported
@@ -75,6 +76,7 @@ struct AttnFusedArgs {
     float *partial;
     unsigned int *counters;
     float *out;
+    uint64_t *trace;
 };
 int launchAttnFused(const AttnFusedArgs &a, cudaStream_t stream, bool pdl);
 

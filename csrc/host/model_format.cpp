@@ -97,8 +97,11 @@ ModelHeader loadModelHeader(const std::string &path, uint32_t maxSeqLen) {
     if (!f) throw std::runtime_error("Cannot open model file (" + path + "): " + std::strerror(errno));
     uint8_t head[8];
     if (std::fread(head, 1, 8, f.get()) != 8) throw std::runtime_error("Cannot read magic value");
-    int32_t headerSize;
+    int32_t magic, headerSize;
+    std::memcpy(&magic, head, 4);
     std::memcpy(&headerSize, head + 4, 4);
+    if (magic == 0xABCD00 || magic == 0xABCD01) throw std::runtime_error("Old model format is not supported");
+    if (magic != kModelMagic) throw std::runtime_error("Unsupported magic number");
     if (headerSize < 8 || headerSize > (1 << 20)) throw std::runtime_error("Cannot read header size");
     std::vector<uint8_t> buf(headerSize);
     std::memcpy(buf.data(), head, 8);

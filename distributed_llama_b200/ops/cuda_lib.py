@@ -53,6 +53,8 @@ def lib() -> C.CDLL:
     L.dl_engine_set_layer.restype = i32
     L.dl_engine_set_globals.argtypes = [vp, C.POINTER(GlobalPtrs)]
     L.dl_engine_set_globals.restype = i32
+    L.dl_engine_set_trace.argtypes = [vp, vp, u32]
+    L.dl_engine_set_trace.restype = i32
     L.dl_engine_num_sms.argtypes = [vp]
     L.dl_engine_num_sms.restype = u32
     L.dl_engine_forward.argtypes = [vp, i32, i32, i32, vp]

@@ -88,6 +88,18 @@ class Engine:
         except Exception:
             pass
 
+    # -- tracing --
+    def enable_trace(self, cap_launches: int = 1024):
+        """Device-side timeline: every kernel stamps globaltimer at entry / dependency resolved / prologue done / exit.
+        Must be enabled before the decode graph is captured."""
+        self.trace_buf = torch.zeros(cap_launches, 4, dtype=torch.int64, device=self.device)
+        cl.check(self._lib.dl_engine_set_trace(self._h, self.trace_buf.data_ptr(), cap_launches), "engine_set_trace")
+        self._graph_ready = False
+
+    def read_trace(self):
+        t = self.trace_buf.cpu().numpy()
+        return t[t[:, 0] != 0]
+
     # -- low level --
     def _set_inputs(self, tokens: Sequence[int], start_pos: int):
         # Pageable source tensors: the copy is staged before the call returns, so back-to-back chunks cannot
