@@ -421,9 +421,11 @@ int gemvQ40Tma(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t st
     TmaGemvGeom geo{};
     geo.maxTileRows = 2 * ((nPairs + grid - 1) / grid);
     const uint32_t rowBytes = nblk * 18;
-    uint32_t sr = (16 * 1024) / rowBytes;
-    sr = sr / 4 * 4;
-    if (sr < 4) sr = rowBytes * 4 <= 20 * 1024 ? 4 : 2;
+    // a stage should hold >= 16 steps (one per consumer warp) so the per-stage barrier traffic is amortised
+    uint32_t sr = (64 + nseg - 1) / nseg;
+    sr = (sr + 3) / 4 * 4;
+    while (sr > 4 && sr * rowBytes > 36 * 1024) sr -= 4;
+    if (sr * rowBytes > 36 * 1024) sr = 2;
     if (sr > 64) sr = 64;
     geo.stageRows = sr;
     geo.stageBytes = (sr * rowBytes + 127) / 128 * 128;
