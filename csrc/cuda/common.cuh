@@ -76,6 +76,24 @@ __device__ __forceinline__ uint32_t ldgStreamU32(const void *p) {
     return r;
 }
 
+// ---- system-scope flag helpers for peer-memory signalling ------------------------------------------------
+__device__ __forceinline__ void stReleaseSys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ldAcquireSys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stRelaxedSysF32(float *p, float v) {
+    asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ldRelaxedSysF32(const float *p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ int dp4a(uint32_t a, uint32_t b, int c) {
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));   // a: unsigned nibbles, b: signed int8

@@ -55,8 +55,15 @@ struct GlobalPtrs {
     unsigned int *argCounter;    // [1]
 };
 
+struct CommPtrs {   // mirrored by ctypes
+    uint32_t nRanks, rank, maxCtas, slotStride;
+    void *arena[kMaxRanks];          // every rank's symmetric arena mapped into this process
+    uint64_t slotsOff, flagsOff, candValOff, candIdxOff, candFlagOff, gatherOff;
+};
+
 struct Engine {
     EngineConfig cfg{};
+    CommPtrs comm{};
     std::vector<LayerPtrs> layers;
     GlobalPtrs g{};
     cudaGraphExec_t decodeGraph = nullptr;
@@ -73,7 +80,24 @@ struct Engine {
         if (_r != 0) return _r;         \
     } while (0)
 
+static void fillAr(const Engine &e, ArArgs &ar, uint32_t parity) {
+    const CommPtrs &c = e.comm;
+    ar.nRanks = c.nRanks; ar.rank = c.rank; ar.parity = parity; ar.maxCtas = c.maxCtas; ar.slotStride = c.slotStride; ar.dim = e.cfg.dim;
+    for (uint32_t r = 0; r < c.nRanks && r < (uint32_t)kMaxRanks; r++) {
+        uint8_t *base = (uint8_t *)c.arena[r];
+        ar.slots[r] = (float *)(base + c.slotsOff);
+        ar.flags[r] = (uint32_t *)(base + c.flagsOff);
+        ar.candVal[r] = (float *)(base + c.candValOff);
+        ar.candIdx[r] = (int *)(base + c.candIdxOff);
+        ar.candFlag[r] = (uint32_t *)(base + c.candFlagOff);
+    }
+}
+
 static int gemvSel(const Engine &e, int pro, int epi, int nb, const GemvArgs &a, int numSms, cudaStream_t stream, bool pdl) {
+    if (a.ar.nRanks > 1) {   // the in-kernel all-reduce lives in the TMA kernel only
+        const int r = gemvQ40Tma(pro, epi, nb, a, numSms, stream, pdl);
+        return r == 1 ? -30 : r;
+    }
     return e.useTma ? gemvQ40Auto(pro, epi, nb, a, numSms, stream, pdl) : gemvQ40(pro, epi, nb, a, numSms, stream, pdl);
 }
 
@@ -120,6 +144,7 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
         a = GemvArgs{};
         a.qs = (const uint32_t *)L.woQs; a.scales = (const __half *)L.woSc; a.d = c.dim; a.n = qDim;
         a.in = e.g.z; a.inStride = qDim; a.out = e.g.x; a.outStride = c.dim; a.trace = nextTrace();
+        if (e.comm.nRanks > 1) fillAr(e, a.ar, 0);
         DL_TRY(gemvSel(e, PRO_PLAIN_, EPI_RESIDUAL_, nb, a, c.numSms, stream, pdl));
         // 5. rmsnorm -> q80 -> W1|W3 -> silu*up
         a = GemvArgs{};
@@ -130,6 +155,7 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
         a = GemvArgs{};
         a.qs = (const uint32_t *)L.w2Qs; a.scales = (const __half *)L.w2Sc; a.d = c.dim; a.n = c.ffDim;
         a.in = e.g.h; a.inStride = c.ffDim; a.out = e.g.x; a.outStride = c.dim; a.trace = nextTrace();
+        if (e.comm.nRanks > 1) fillAr(e, a.ar, 1);
         DL_TRY(gemvSel(e, PRO_PLAIN_, EPI_RESIDUAL_, nb, a, c.numSms, stream, pdl));
     }
     if (logitsMode != 0) {
@@ -143,7 +169,8 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
                 // logits + greedy sampling + position advance in one launch
                 a.argVal = e.g.argVal; a.argIdx = e.g.argIdx; a.argCounter = e.g.argCounter;
                 a.tokenOut = e.g.tokens; a.posInOut = e.g.pos; a.history = e.g.history; a.historyCap = c.seqLen;
-                a.rowOffsetGlobal = 0;
+                a.rowOffsetGlobal = c.rank * c.vocab;
+                if (e.comm.nRanks > 1) fillAr(e, a.ar, 0);
                 r = gemvQ40Tma(PRO_RMSNORM_, EPI_ARGMAX_, 1, a, c.numSms, stream, pdl);
                 if (r < 0) return r;
             }
@@ -199,6 +226,11 @@ DL_EXPORT int dl_engine_set_layer(void *h, uint32_t layer, const dl::LayerPtrs *
 
 DL_EXPORT int dl_engine_set_globals(void *h, const dl::GlobalPtrs *p) {
     ((Engine *)h)->g = *p;
+    return 0;
+}
+
+DL_EXPORT int dl_engine_set_comm(void *h, const dl::CommPtrs *p) {
+    ((Engine *)h)->comm = *p;
     return 0;
 }
 

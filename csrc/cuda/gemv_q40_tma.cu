@@ -315,6 +315,42 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
     } else {
         float best = -INFINITY;
         int bestIdx = 0x7fffffff;
+        if (EPI == EPI_RESIDUAL && a.ar.nRanks > 1) {
+            // ---- fused one-shot all-reduce over NVLink peer memory + residual add -------------------------------
+            // Every rank computed the partial product of the same row tile in the CTA with the same index. Push the
+            // partial rows into slot[myRank] of *every* rank (peer stores), raise one flag per destination, wait for
+            // the flags of all sources, then sum the slots in rank order (bit-identical result on every rank).
+            const ArArgs &ar = a.ar;
+            const size_t slotBase = (size_t)(ar.parity * ar.nRanks + ar.rank) * ar.slotStride;
+            for (uint32_t i = tid; i < tileRows * NB; i += kConsumerThreads) {
+                const uint32_t r = i / NB, t = i - r * NB;
+                float v = 0.f;
+                for (uint32_t sg = 0; sg < nseg; sg++) v += partial[((size_t)r * nseg + sg) * NB + t];
+                const size_t off = slotBase + (size_t)t * ar.dim + rowBase + r;
+#pragma unroll 1
+                for (uint32_t p = 0; p < ar.nRanks; p++) stRelaxedSysF32(ar.slots[(ar.rank + p) % ar.nRanks] + off, v);
+            }
+            __threadfence_system();
+            consumerBarrier();
+            const size_t flagRow = (size_t)ar.parity * ar.nRanks;
+            if (tid < ar.nRanks) stReleaseSys(ar.flags[tid] + (flagRow + ar.rank) * ar.maxCtas + blockIdx.x, 1u);
+            uint32_t *myFlags = ar.flags[ar.rank];
+            if (tid < ar.nRanks) {
+                const uint32_t *f = myFlags + (flagRow + tid) * ar.maxCtas + blockIdx.x;
+                while (ldAcquireSys(f) == 0u) { }
+            }
+            consumerBarrier();
+            const float *mine = ar.slots[ar.rank];
+            for (uint32_t i = tid; i < tileRows * NB; i += kConsumerThreads) {
+                const uint32_t r = i / NB, t = i - r * NB;
+                float sum = 0.f;
+                for (uint32_t sr = 0; sr < ar.nRanks; sr++)
+                    sum += ldRelaxedSysF32(mine + (size_t)(ar.parity * ar.nRanks + sr) * ar.slotStride + (size_t)t * ar.dim + rowBase + r);
+                a.out[(size_t)t * a.outStride + rowBase + r] += sum;
+            }
+            consumerBarrier();
+            if (tid < ar.nRanks) myFlags[(flagRow + tid) * ar.maxCtas + blockIdx.x] = 0u;   // re-arm for the all-reduce after next
+        } else
         for (uint32_t i = tid; i < tileRows * NB; i += kConsumerThreads) {
             const uint32_t r = i / NB, t = i - r * NB;
             float v = 0.f;
@@ -377,6 +413,33 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
                     const float ov = __shfl_xor_sync(0xffffffffu, best, o);
                     const int oi = __shfl_xor_sync(0xffffffffu, bestIdx, o);
                     if (better(ov, oi, best, bestIdx)) { best = ov; bestIdx = oi; }
+                }
+                if (a.ar.nRanks > 1) {
+                    // vocabulary-parallel logits: exchange the per-rank winners over peer memory; every rank then
+                    // picks the same global token, so no token broadcast is needed afterwards
+                    const ArArgs &ar = a.ar;
+                    if (lane < ar.nRanks) {
+                        stRelaxedSysF32(ar.candVal[lane] + ar.rank, best);
+                        asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(ar.candIdx[lane] + ar.rank), "r"(bestIdx) : "memory");
+                    }
+                    __threadfence_system();
+                    __syncwarp();
+                    if (lane < ar.nRanks) stReleaseSys(ar.candFlag[lane] + ar.rank, 1u);
+                    if (lane < ar.nRanks) {
+                        while (ldAcquireSys(ar.candFlag[ar.rank] + lane) == 0u) { }
+                        best = ldRelaxedSysF32(ar.candVal[ar.rank] + lane);
+                        asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(bestIdx) : "l"(ar.candIdx[ar.rank] + lane) : "memory");
+                        ar.candFlag[ar.rank][lane] = 0u;
+                    } else {
+                        best = -INFINITY;
+                        bestIdx = 0x7fffffff;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bestIdx, o);
+                        if (better(ov, oi, best, bestIdx)) { best = ov; bestIdx = oi; }
+                    }
                 }
                 if (lane == 0) {
                     a.tokenOut[0] = bestIdx;

@@ -7,6 +7,20 @@ namespace dl {
 enum { PRO_RMSNORM_ = 0, PRO_PLAIN_ = 1 };
 enum { EPI_STORE_ = 0, EPI_RESIDUAL_ = 1, EPI_SWIGLU_ = 2, EPI_ARGMAX_ = 3 };
 
+// In-kernel one-shot all-reduce over NVLink peer memory (see the EPI_RESIDUAL epilogue of gemv_q40_tma.cu).
+constexpr int kMaxRanks = 8;
+struct ArArgs {
+    uint32_t nRanks, rank, parity, maxCtas;
+    uint32_t slotStride;          // floats per (parity, source rank) slot = maxBatch * dim
+    uint32_t dim;                 // floats between tokens inside a slot
+    float *slots[kMaxRanks];      // rank r's slot area, mapped into this process: [2][nRanks][slotStride]
+    uint32_t *flags[kMaxRanks];   // rank r's flag area: [2][nRanks][maxCtas]
+    // cross-rank arg-max (EPI_ARGMAX)
+    float *candVal[kMaxRanks];    // rank r's candidate arrays: [nRanks]
+    int *candIdx[kMaxRanks];
+    uint32_t *candFlag[kMaxRanks];
+};
+
 struct GemvArgs {
     const uint32_t *qs;
     const __half *scales;
@@ -29,6 +43,7 @@ struct GemvArgs {
     uint32_t historyCap;
     uint32_t rowOffsetGlobal; // added to row indices (vocab slice offset under tensor parallelism)
     uint64_t *trace;          // optional 4-slot timeline record for this launch
+    ArArgs ar;                // ar.nRanks > 1: EPI_RESIDUAL sums the partial products of all ranks before the residual add
 };
 int gemvQ40(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl);      // per-thread loads (fallback)
 int gemvQ40Tma(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl);   // TMA ring; returns 1 if shape unsupported

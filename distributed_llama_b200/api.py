@@ -44,8 +44,7 @@ class InferenceSession:
             device = f"cuda:{torch.cuda.current_device()}"
         self.device = torch.device(device)
         self.weights = load_device_weights(self.model_file, rank, n_ranks, self.device)
-        self.engine = Engine(self.weights, max_batch=max_batch, use_pdl=use_pdl, comm=comm) if comm is not None else \
-            Engine(self.weights, max_batch=max_batch, use_pdl=use_pdl)
+        self.engine = Engine(self.weights, max_batch=max_batch, use_pdl=use_pdl, comm=comm)
         H = host()
         self.tokenizer = H.Tokenizer(tokenizer_path) if tokenizer_path else None
         vocab = self.tokenizer.vocab_size if self.tokenizer else self.header.vocab_size

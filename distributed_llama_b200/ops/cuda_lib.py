@@ -33,6 +33,12 @@ class GlobalPtrs(C.Structure):
                 ("argVal", vp), ("argIdx", vp), ("argCounter", vp)]
 
 
+class CommPtrs(C.Structure):
+    _fields_ = [("nRanks", u32), ("rank", u32), ("maxCtas", u32), ("slotStride", u32), ("arena", vp * 8),
+                ("slotsOff", u64), ("flagsOff", u64), ("candValOff", u64), ("candIdxOff", u64), ("candFlagOff", u64),
+                ("gatherOff", u64)]
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
@@ -53,6 +59,12 @@ def lib() -> C.CDLL:
     L.dl_engine_set_layer.restype = i32
     L.dl_engine_set_globals.argtypes = [vp, C.POINTER(GlobalPtrs)]
     L.dl_engine_set_globals.restype = i32
+    L.dl_engine_set_comm.argtypes = [vp, C.POINTER(CommPtrs)]
+    L.dl_engine_set_comm.restype = i32
+    for name, args in (("dl_comm_alloc", [C.c_size_t, C.POINTER(vp)]), ("dl_comm_free", [vp]), ("dl_comm_ipc_handle", [vp, vp]),
+                       ("dl_comm_ipc_open", [vp, C.POINTER(vp)]), ("dl_comm_ipc_close", [vp]), ("dl_comm_memset", [vp, i32, C.c_size_t, vp])):
+        getattr(L, name).argtypes = args
+        getattr(L, name).restype = i32
     L.dl_engine_set_trace.argtypes = [vp, vp, u32]
     L.dl_engine_set_trace.restype = i32
     L.dl_engine_num_sms.argtypes = [vp]

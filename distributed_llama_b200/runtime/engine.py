@@ -23,7 +23,7 @@ def _p(t: Optional[torch.Tensor]):
 
 class Engine:
     def __init__(self, weights: DeviceWeights, max_batch: int = 8, n_splits: int = 0, use_pdl: bool = True,
-                 seq_len: Optional[int] = None):
+                 seq_len: Optional[int] = None, comm=None):
         self.w = w = weights
         h = w.header
         dev = w.embedding.device
@@ -76,6 +76,12 @@ class Engine:
                            history=_p(self.history), expertIdx=_p(self.expert_idx), expertWeight=_p(self.expert_weight),
                            argVal=_p(self.arg_val), argIdx=_p(self.arg_idx), argCounter=_p(self.arg_counter))
         cl.check(self._lib.dl_engine_set_globals(self._h, C.byref(gp)), "engine_set_globals")
+        self.comm = comm
+        if comm is not None and comm.world_size > 1:
+            from ..parallel.comm import arena_layout
+            comm.alloc_arena(arena_layout(comm.world_size, max_batch, h.dim, h.vocab_size))
+            cp = comm.comm_ptrs(max_batch * h.dim)
+            cl.check(self._lib.dl_engine_set_comm(self._h, C.byref(cp)), "engine_set_comm")
         self._graph_ready = False
         self._stage_tok = torch.zeros(max_batch, dtype=torch.int32).pin_memory()
         self._stage_pos = torch.zeros(max_batch, dtype=torch.int32).pin_memory()
@@ -128,16 +134,22 @@ class Engine:
             last = i + n == len(tokens)
             self.forward_batch(tokens[i:i + n], start_pos + i, logits_mode=1 if (last and want_logits) else 0)
             i += n
-        return self.logits[0] if want_logits else None
+        return self._full_logits(self.logits[0]) if want_logits else None
 
     def step(self, token: int, pos: int) -> torch.Tensor:
+        """Forward of one token; returns the full-vocabulary logits row (gathered over ranks under tensor parallelism)."""
         self.forward_batch([token], pos, logits_mode=1)
-        return self.logits[0]
+        return self._full_logits(self.logits[0])
+
+    def _full_logits(self, local: torch.Tensor) -> torch.Tensor:
+        if self.comm is None or self.comm.world_size == 1:
+            return local
+        return self.comm.all_gather_cat(local, dim=-1)
 
     def logits_all(self, tokens: Sequence[int], start_pos: int) -> torch.Tensor:
         """Logits for every token of a (<= max_batch, power of two) batch — used by perplexity and tests."""
         self.forward_batch(tokens, start_pos, logits_mode=2)
-        return self.logits[: len(tokens)]
+        return self._full_logits(self.logits[: len(tokens)])
 
     # -- device-resident greedy decoding --
     def run_decode_step(self, use_graph: bool = True):
