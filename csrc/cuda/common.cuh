@@ -94,6 +94,17 @@ __device__ __forceinline__ float ldRelaxedSysF32(const float *p) {
     return v;
 }
 
+// LL ("low latency") words: 4 bytes of payload + a 4-byte valid flag travel in one 8-byte store, which the fabric
+// delivers atomically — the receiver polls the word itself, no fence / separate flag round trip is needed.
+__device__ __forceinline__ void stLL(uint64_t *p, uint32_t payload, uint32_t flag) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(flag) : "memory");
+}
+__device__ __forceinline__ uint2 ldLL(const uint64_t *p) {
+    uint2 v;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ int dp4a(uint32_t a, uint32_t b, int c) {
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));   // a: unsigned nibbles, b: signed int8

@@ -85,11 +85,8 @@ static void fillAr(const Engine &e, ArArgs &ar, uint32_t parity) {
     ar.nRanks = c.nRanks; ar.rank = c.rank; ar.parity = parity; ar.maxCtas = c.maxCtas; ar.slotStride = c.slotStride; ar.dim = e.cfg.dim;
     for (uint32_t r = 0; r < c.nRanks && r < (uint32_t)kMaxRanks; r++) {
         uint8_t *base = (uint8_t *)c.arena[r];
-        ar.slots[r] = (float *)(base + c.slotsOff);
-        ar.flags[r] = (uint32_t *)(base + c.flagsOff);
-        ar.candVal[r] = (float *)(base + c.candValOff);
-        ar.candIdx[r] = (int *)(base + c.candIdxOff);
-        ar.candFlag[r] = (uint32_t *)(base + c.candFlagOff);
+        ar.slots[r] = (uint64_t *)(base + c.slotsOff);
+        ar.cand[r] = (uint64_t *)(base + c.candValOff);
     }
 }
 

@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
             // Every rank computed the partial product of the same row tile in the CTA with the same index. Push the
             // partial rows into slot[myRank] of *every* rank (peer stores), raise one flag per destination, wait for
             // the flags of all sources, then sum the slots in rank order (bit-identical result on every rank).
+            // LL protocol: every 8-byte word carries (partial value, valid flag); receivers poll the words and clear them.
             const ArArgs &ar = a.ar;
             const size_t slotBase = (size_t)(ar.parity * ar.nRanks + ar.rank) * ar.slotStride;
             for (uint32_t i = tid; i < tileRows * NB; i += kConsumerThreads) {
@@ -328,28 +329,21 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
                 for (uint32_t sg = 0; sg < nseg; sg++) v += partial[((size_t)r * nseg + sg) * NB + t];
                 const size_t off = slotBase + (size_t)t * ar.dim + rowBase + r;
 #pragma unroll 1
-                for (uint32_t p = 0; p < ar.nRanks; p++) stRelaxedSysF32(ar.slots[(ar.rank + p) % ar.nRanks] + off, v);
+                for (uint32_t p = 0; p < ar.nRanks; p++) stLL(ar.slots[(ar.rank + p) % ar.nRanks] + off, __float_as_uint(v), 1u);
             }
-            __threadfence_system();
-            consumerBarrier();
-            const size_t flagRow = (size_t)ar.parity * ar.nRanks;
-            if (tid < ar.nRanks) stReleaseSys(ar.flags[tid] + (flagRow + ar.rank) * ar.maxCtas + blockIdx.x, 1u);
-            uint32_t *myFlags = ar.flags[ar.rank];
-            if (tid < ar.nRanks) {
-                const uint32_t *f = myFlags + (flagRow + tid) * ar.maxCtas + blockIdx.x;
-                while (ldAcquireSys(f) == 0u) { }
-            }
-            consumerBarrier();
-            const float *mine = ar.slots[ar.rank];
+            uint64_t *mine = ar.slots[ar.rank];
             for (uint32_t i = tid; i < tileRows * NB; i += kConsumerThreads) {
                 const uint32_t r = i / NB, t = i - r * NB;
                 float sum = 0.f;
-                for (uint32_t sr = 0; sr < ar.nRanks; sr++)
-                    sum += ldRelaxedSysF32(mine + (size_t)(ar.parity * ar.nRanks + sr) * ar.slotStride + (size_t)t * ar.dim + rowBase + r);
+                for (uint32_t sr = 0; sr < ar.nRanks; sr++) {
+                    uint64_t *w = mine + (size_t)(ar.parity * ar.nRanks + sr) * ar.slotStride + (size_t)t * ar.dim + rowBase + r;
+                    uint2 v = ldLL(w);
+                    while (v.y == 0u) v = ldLL(w);
+                    sum += __uint_as_float(v.x);              // fixed rank order: bit-identical on every rank
+                    stLL(w, 0u, 0u);                          // re-arm for the all-reduce after next (double buffered)
+                }
                 a.out[(size_t)t * a.outStride + rowBase + r] += sum;
             }
-            consumerBarrier();
-            if (tid < ar.nRanks) myFlags[(flagRow + tid) * ar.maxCtas + blockIdx.x] = 0u;   // re-arm for the all-reduce after next
         } else
         for (uint32_t i = tid; i < tileRows * NB; i += kConsumerThreads) {
             const uint32_t r = i / NB, t = i - r * NB;
@@ -418,18 +412,14 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
                     // vocabulary-parallel logits: exchange the per-rank winners over peer memory; every rank then
                     // picks the same global token, so no token broadcast is needed afterwards
                     const ArArgs &ar = a.ar;
+                    if (lane < ar.nRanks) stLL(ar.cand[lane] + ar.rank, __float_as_uint(best), (uint32_t)bestIdx + 1u);
                     if (lane < ar.nRanks) {
-                        stRelaxedSysF32(ar.candVal[lane] + ar.rank, best);
-                        asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(ar.candIdx[lane] + ar.rank), "r"(bestIdx) : "memory");
-                    }
-                    __threadfence_system();
-                    __syncwarp();
-                    if (lane < ar.nRanks) stReleaseSys(ar.candFlag[lane] + ar.rank, 1u);
-                    if (lane < ar.nRanks) {
-                        while (ldAcquireSys(ar.candFlag[ar.rank] + lane) == 0u) { }
-                        best = ldRelaxedSysF32(ar.candVal[ar.rank] + lane);
-                        asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(bestIdx) : "l"(ar.candIdx[ar.rank] + lane) : "memory");
-                        ar.candFlag[ar.rank][lane] = 0u;
+                        uint64_t *w = ar.cand[ar.rank] + lane;
+                        uint2 v = ldLL(w);
+                        while (v.y == 0u) v = ldLL(w);
+                        best = __uint_as_float(v.x);
+                        bestIdx = (int)(v.y - 1u);
+                        stLL(w, 0u, 0u);
                     } else {
                         best = -INFINITY;
                         bestIdx = 0x7fffffff;

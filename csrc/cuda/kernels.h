@@ -11,14 +11,10 @@ enum { EPI_STORE_ = 0, EPI_RESIDUAL_ = 1, EPI_SWIGLU_ = 2, EPI_ARGMAX_ = 3 };
 constexpr int kMaxRanks = 8;
 struct ArArgs {
     uint32_t nRanks, rank, parity, maxCtas;
-    uint32_t slotStride;          // floats per (parity, source rank) slot = maxBatch * dim
-    uint32_t dim;                 // floats between tokens inside a slot
-    float *slots[kMaxRanks];      // rank r's slot area, mapped into this process: [2][nRanks][slotStride]
-    uint32_t *flags[kMaxRanks];   // rank r's flag area: [2][nRanks][maxCtas]
-    // cross-rank arg-max (EPI_ARGMAX)
-    float *candVal[kMaxRanks];    // rank r's candidate arrays: [nRanks]
-    int *candIdx[kMaxRanks];
-    uint32_t *candFlag[kMaxRanks];
+    uint32_t slotStride;          // words per (parity, source rank) slot = maxBatch * dim
+    uint32_t dim;                 // words between tokens inside a slot
+    uint64_t *slots[kMaxRanks];   // rank r's LL slot area, mapped into this process: [2][nRanks][slotStride] x (f32 payload, flag)
+    uint64_t *cand[kMaxRanks];    // rank r's arg-max candidates: [nRanks] x (f32 value, index + 1)
 };
 
 struct GemvArgs {

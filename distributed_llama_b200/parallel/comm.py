@@ -33,9 +33,9 @@ def arena_layout(n_ranks: int, max_batch: int, dim: int, vocab_full: int) -> Are
     def align(x):
         return (x + 255) // 256 * 256
     off = 0
-    slots = off; off = align(off + 2 * n_ranks * max_batch * dim * 4)
+    slots = off; off = align(off + 2 * n_ranks * max_batch * dim * 8)   # LL words: (f32 payload, flag)
     flags = off; off = align(off + 2 * n_ranks * MAX_CTAS * 4)
-    cv = off; off = align(off + 64)
+    cv = off; off = align(off + 8 * 8)                                   # arg-max candidates, one LL word per rank
     ci = off; off = align(off + 64)
     cf = off; off = align(off + 64)
     gather = off; off = align(off + max_batch * vocab_full * 4)

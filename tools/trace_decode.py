@@ -7,8 +7,19 @@ from bench import ensure_model
 from distributed_llama_b200.api import InferenceSession
 
 model = sys.argv[1] if len(sys.argv) > 1 else "llama-3.1-8b"
+comm = None
+rank = int(os.environ.get("RANK", "0"))
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    import torch.distributed as dist
+    from distributed_llama_b200.parallel.comm import Communicator
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{os.environ['LOCAL_RANK']}"))
+    comm = Communicator()
+    if rank == 0:
+        ensure_model(model)
+    dist.barrier()
 m, t = ensure_model(model)
-sess = InferenceSession(m, t, max_seq_len=2048)
+sess = InferenceSession(m, t, max_seq_len=2048, comm=comm)
 eng = sess.engine
 eng.enable_trace(4096)
 prompt = [(7 * i + 3) % 1000 + 1 for i in range(64)]
@@ -19,6 +30,8 @@ eng.trace_buf.zero_()
 eng.decode_greedy(prompt[-1], 63, 1)
 torch.cuda.synchronize()
 tr = eng.read_trace().astype(np.float64)
+if rank != 0:
+    sys.exit(0)
 t0 = tr[:, 0].min()
 names = ["qkv", "attn", "wo", "w13", "w2"]
 print("slot name   entry  waitdone prologue  exit | dur  gap_from_prev_exit  (us)")
