@@ -1,0 +1,394 @@
+// Prefill GEMM on the 5th-generation tensor cores: out[T][d] = act_bf16[T][n] · dequant(W_q40[d][n])^T, T <= 256.
+//
+// Reference path replaced: batched OP_MATMUL via llamafile tinyBLAS (Q40×Q80 on CPU vector units,
+// src/nn/nn-cpu-ops.cpp:1120-1136, src/nn/llamafile/sgemm.cpp:455-783) for the 32-token prefill chunks.
+//
+// sm_100a design (swap-AB: the 128 weight rows fill the UMMA M dimension, the tokens sit on N):
+//   warp 0      TMA producer   — activations tile [nTile tokens x 64 k] per stage via cp.async.bulk.tensor (SWIZZLE_128B)
+//   warp 1      MMA issuer     — one elected lane issues 4 x tcgen05.mma (M=128, N=nTile, K=16, bf16 -> f32 TMEM) per stage,
+//                                tcgen05.commit releases the stage / publishes the accumulator
+//   warp 2      TMEM allocator — 2 accumulator buffers (epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 4-7   epilogue       — tcgen05.ld (32 lanes x 16 columns), fused residual-add / SwiGLU / store
+//   warps 8-15  dequant        — q40 nibbles + fp16 scale -> bf16, written straight into the canonical K-major
+//                                SWIZZLE_128B UMMA tile in shared memory (generic proxy), fence.proxy.async, mbarrier arrive.
+//                                This is the "q40 dequant fused into the GEMM prologue": the weights are never materialised
+//                                in bf16 in global memory, HBM traffic stays at 4.5 bits/weight.
+// Persistent CTAs loop over 128-row tiles; all synchronisation is mbarrier based (no __syncthreads in the main loop).
+#include <cuda.h>
+
+#include "kernels.h"
+
+namespace dl {
+
+constexpr int kGmBlockM = 128;
+constexpr int kGmBlockK = 64;
+constexpr int kGmThreads = 512;
+constexpr int kGmDeqWarps = 8;
+constexpr int kGmMaxStages = 8;
+constexpr int kGmATileBytes = kGmBlockM * kGmBlockK * 2;   // 16 KB
+
+enum { GEPI_STORE_F32 = 0, GEPI_RESIDUAL = 1, GEPI_SWIGLU_BF16 = 2, GEPI_STORE_BF16 = 3 };
+
+struct GemmArgs {
+    const uint32_t *qs;
+    const __half *scales;
+    uint32_t d, n;        // weight rows / columns
+    uint32_t T, nTile;    // tokens, tokens rounded up to 16
+    void *out;
+    uint32_t outStride;   // elements between tokens
+    uint32_t stages, tmemCols;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gmBarInit(uint64_t *b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sAddr(b)), "r"(c) : "memory"); }
+__device__ __forceinline__ void gmBarExpectTx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sAddr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gmBarArrive(uint64_t *b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sAddr(b)) : "memory"); }
+__device__ __forceinline__ void gmBarWait(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nGM_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra GM_DONE;\nbra GM_WAIT;\nGM_DONE:\n}\n" ::"r"(sAddr(b)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tmaLoad2d(void *dst, const CUtensorMap *map, uint32_t c0, uint32_t c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(sAddr(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(sAddr(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmemD), "l"(descA),
+        "l"(descB), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void ummaCommit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void tmemLoad16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart), sm_100 descriptor version 1.
+__device__ __forceinline__ uint64_t makeSmemDesc(uint32_t smemAddrBytes) {
+    return (uint64_t)((smemAddrBytes >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcKernel(const __grid_constant__ CUtensorMap tmapB, GemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t smemRaw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nTile = a.nTile;
+    const uint32_t bTileBytes = nTile * 128;
+    const uint32_t stageBytes = kGmATileBytes + bTileBytes;
+    uint64_t *fullBar = reinterpret_cast<uint64_t *>(smem + (size_t)a.stages * stageBytes);
+    uint64_t *emptyBar = fullBar + kGmMaxStages;
+    uint64_t *tmemFull = emptyBar + kGmMaxStages;     // [2]
+    uint64_t *tmemEmpty = tmemFull + 2;               // [2]
+    uint32_t *tmemBasePtr = reinterpret_cast<uint32_t *>(tmemEmpty + 2);
+
+    const uint32_t nblk = a.n / 32;
+    const uint32_t nkb = a.n / kGmBlockK;
+    const uint32_t nTilesM = (a.d + kGmBlockM - 1) / kGmBlockM;
+
+    pdlLaunchDependents();
+    if (tid == 0) {
+        for (uint32_t s = 0; s < a.stages; s++) {
+            gmBarInit(&fullBar[s], 1 + kGmDeqWarps);
+            gmBarInit(&emptyBar[s], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            gmBarInit(&tmemFull[i], 1);
+            gmBarInit(&tmemEmpty[i], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sAddr(tmemBasePtr)), "r"(a.tmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    const uint32_t tmemBase = *tmemBasePtr;
+    pdlWait();   // activations (and the residual stream) come from the predecessor kernel
+
+    if (warp == 0) {
+        // ===================== TMA producer: activation tiles =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x) {
+                for (uint32_t kb = 0; kb < nkb; kb++, it++) {
+                    const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                    gmBarWait(&emptyBar[s], ph ^ 1);
+                    gmBarExpectTx(&fullBar[s], bTileBytes);
+                    tmaLoad2d(smem + (size_t)s * stageBytes + kGmATileBytes, &tmapB, kb * kGmBlockK, 0, &fullBar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((nTile >> 3) << 17) | ((uint32_t)(kGmBlockM >> 4) << 24);
+        uint32_t it = 0, tcount = 0;
+        for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x, tcount++) {
+            const uint32_t acc = tcount & 1, accPh = (tcount >> 1) & 1;
+            gmBarWait(&tmemEmpty[acc], accPh ^ 1);
+            tcFenceAfter();
+            const uint32_t tmemD = tmemBase + acc * nTile;
+            for (uint32_t kb = 0; kb < nkb; kb++, it++) {
+                const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                gmBarWait(&fullBar[s], ph);
+                tcFenceAfter();
+                if (lane == 0) {
+                    const uint32_t aAddr = sAddr(smem + (size_t)s * stageBytes);
+                    const uint64_t descA = makeSmemDesc(aAddr);
+                    const uint64_t descB = makeSmemDesc(aAddr + kGmATileBytes);
+#pragma unroll
+                    for (uint32_t k = 0; k < kGmBlockK / 16; k++)
+                        umma(tmemD, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);   // +32 B per K=16 slice
+                    ummaCommit(&emptyBar[s]);
+                    if (kb == nkb - 1) ummaCommit(&tmemFull[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== epilogue =====================
+        const uint32_t q = warp - 4;
+        uint32_t tcount = 0;
+        for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x, tcount++) {
+            const uint32_t acc = tcount & 1, accPh = (tcount >> 1) & 1;
+            gmBarWait(&tmemFull[acc], accPh);
+            tcFenceAfter();
+            const uint32_t f = tile * kGmBlockM + q * 32 + lane;     // output feature owned by this thread (= TMEM lane)
+            const bool fOk = f < a.d;
+            for (uint32_t c0 = 0; c0 < nTile; c0 += 16) {
+                uint32_t r[16];
+                tmemLoad16(tmemBase + ((q * 32u) << 16) + acc * nTile + c0, r);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint32_t tok = c0 + j;
+                    const float v = __uint_as_float(r[j]);
+                    if (EPI == GEPI_SWIGLU_BF16) {
+                        const float other = __shfl_xor_sync(0xffffffffu, v, 1);   // rows (2i, 2i+1) = (gate_i, up_i)
+                        if (tok < a.T && fOk && !(lane & 1))
+                            reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(siluf(v) * other);
+                    } else if (tok < a.T && fOk) {
+                        if (EPI == GEPI_STORE_F32) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v;
+                        if (EPI == GEPI_RESIDUAL) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] += v;
+                        if (EPI == GEPI_STORE_BF16) reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + f] = __float2bfloat16_rn(v);
+                    }
+                }
+            }
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) gmBarArrive(&tmemEmpty[acc]);
+        }
+    } else if (warp >= 8) {
+        // ===================== dequant: q40 -> bf16 UMMA tile =====================
+        const uint32_t dt = tid - 256;
+        const uint32_t row = dt & 127, b = dt >> 7;                 // 128 rows x 2 quant blocks per 64-wide k slice
+        const uint32_t swz = row & 7;
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x) {
+            const uint32_t rowG = tile * kGmBlockM + row;
+            const bool ok = rowG < a.d;
+            const uint4 *qrow = reinterpret_cast<const uint4 *>(a.qs) + (size_t)rowG * nblk + b;
+            const __half *srow = a.scales + (size_t)rowG * nblk + b;
+            constexpr int G = 4;   // k-blocks per prefetch group
+            uint4 curQ[G], nxtQ[G];
+            uint16_t curS[G], nxtS[G];
+            auto loadGroup = [&](uint32_t kb0, uint4 (&Q)[G], uint16_t (&S)[G]) {
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const uint32_t kb = kb0 + g;
+                    if (ok && kb < nkb) {
+                        Q[g] = ldgStream16(qrow + (size_t)kb * 2);
+                        S[g] = ldgStreamU16(srow + (size_t)kb * 2);
+                    } else {
+                        Q[g] = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);   // nibble 8 == value 0
+                        S[g] = 0;
+                    }
+                }
+            };
+            loadGroup(0, curQ, curS);
+            for (uint32_t kb0 = 0; kb0 < nkb; kb0 += G) {
+                if (kb0 + G < nkb) loadGroup(kb0 + G, nxtQ, nxtS);
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const uint32_t kb = kb0 + g;
+                    if (kb < nkb) {
+                        const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                        gmBarWait(&emptyBar[s], ph ^ 1);
+                        uint8_t *aTile = smem + (size_t)s * stageBytes;
+                        const __nv_bfloat16 sc = __float2bfloat16_rn(__half2float(__ushort_as_half(curS[g])));
+                        const __nv_bfloat162 sc2 = __halves2bfloat162(sc, sc);
+                        const __nv_bfloat162 off = __floats2bfloat162_rn(136.f, 136.f);
+                        const uint32_t w[4] = {curQ[g].x, curQ[g].y, curQ[g].z, curQ[g].w};
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int sft = 0; sft < 4; sft++) {
+                                // (nibble | 0x4300) is the bf16 value 128 + nibble; subtract 136 -> nibble - 8 (exact), then scale
+                                uint32_t t = ((w[c] >> (4 * sft)) & 0x000f000fu) | 0x43004300u;
+                                __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162 *>(&t);
+                                v = __hmul2(__hsub2(v, off), sc2);
+                                o[sft] = *reinterpret_cast<uint32_t *>(&v);
+                            }
+                            const uint32_t chunk = (b * 4 + c) ^ swz;                       // SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
+                            *reinterpret_cast<uint4 *>(aTile + row * 128 + chunk * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+                        __syncwarp();
+                        if (lane == 0) gmBarArrive(&fullBar[s]);
+                        it++;
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) { curQ[g] = nxtQ[g]; curS[g] = nxtS[g]; }
+            }
+        }
+    }
+
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == 2) {
+        tcFenceAfter();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(a.tmemCols) : "memory");
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encodeTiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <int EPI>
+static int launchGemm(const CUtensorMap &map, const GemmArgs &a, int grid, size_t smemBytes, cudaStream_t stream, bool pdl) {
+    auto kernel = gemmQ40TcKernel<EPI>;
+    static size_t configured = 0;
+    if (smemBytes > configured) {
+        DL_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        configured = smemBytes;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGmThreads);
+    cfg.dynamicSmemBytes = smemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, map, a));
+    return 0;
+}
+
+// act: bf16 [T][n] row-major (row stride actStride elements). Returns <0 on error.
+int gemmQ40Tc(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T,
+              void *out, uint32_t outStride, int numSms, cudaStream_t stream, bool pdl) {
+    if (T == 0 || T > 256 || n % kGmBlockK || d % 2) return -1;
+    EncodeTiledFn enc = encodeTiled();
+    if (!enc) return -2;
+    GemmArgs a{};
+    a.qs = (const uint32_t *)qs; a.scales = (const __half *)scales; a.d = d; a.n = n; a.T = T;
+    a.nTile = (T + 15) / 16 * 16;
+    a.out = out; a.outStride = outStride;
+    uint32_t cols = 32;
+    while (cols < 2 * a.nTile) cols *= 2;
+    a.tmemCols = cols;
+    const size_t stageBytes = kGmATileBytes + (size_t)a.nTile * 128;
+    uint32_t stages = (uint32_t)((200 * 1024) / stageBytes);
+    if (stages > (uint32_t)kGmMaxStages) stages = kGmMaxStages;
+    if (stages < 2) return -3;
+    a.stages = stages;
+    const size_t smemBytes = stages * stageBytes + 1024 + 512;
+
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {n, T};
+    const cuuint64_t strides[1] = {(cuuint64_t)actStride * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kGmBlockK, a.nTile};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(act), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -4;
+    const uint32_t nTilesM = (d + kGmBlockM - 1) / kGmBlockM;
+    const int grid = (int)(nTilesM < (uint32_t)numSms ? nTilesM : (uint32_t)numSms);
+    switch (epi) {
+        case GEPI_STORE_F32: return launchGemm<GEPI_STORE_F32>(map, a, grid, smemBytes, stream, pdl);
+        case GEPI_RESIDUAL: return launchGemm<GEPI_RESIDUAL>(map, a, grid, smemBytes, stream, pdl);
+        case GEPI_SWIGLU_BF16: return launchGemm<GEPI_SWIGLU_BF16>(map, a, grid, smemBytes, stream, pdl);
+        case GEPI_STORE_BF16: return launchGemm<GEPI_STORE_BF16>(map, a, grid, smemBytes, stream, pdl);
+    }
+    return -5;
+}
+
+// ---- rmsnorm -> bf16 (activation operand producer) ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rmsNormBf16Kernel(const float *__restrict__ x, uint32_t xStride, const float *__restrict__ w,
+                                                         __nv_bfloat16 *__restrict__ y, uint32_t yStride, uint32_t n, float eps) {
+    pdlLaunchDependents();
+    pdlWait();
+    __shared__ float red[8];
+    const float4 *x4 = reinterpret_cast<const float4 *>(x + (size_t)blockIdx.x * xStride);
+    float ss = 0.f;
+    for (uint32_t i = threadIdx.x; i < n / 4; i += 256) {
+        const float4 v = x4[i];
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warpSum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < 8; i++) tot += red[i];
+    const float inv = rsqrtf(tot / (float)n + eps);
+    __nv_bfloat162 *y2 = reinterpret_cast<__nv_bfloat162 *>(y + (size_t)blockIdx.x * yStride);
+    for (uint32_t i = threadIdx.x; i < n / 4; i += 256) {
+        const float4 v = x4[i];
+        const float4 ww = w ? reinterpret_cast<const float4 *>(w)[i] : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float s = w ? inv : 1.f;
+        y2[2 * i] = __floats2bfloat162_rn(ww.x * (v.x * s), ww.y * (v.y * s));
+        y2[2 * i + 1] = __floats2bfloat162_rn(ww.z * (v.z * s), ww.w * (v.w * s));
+    }
+}
+
+int launchRmsNormBf16(const float *x, uint32_t xStride, const float *w, void *y, uint32_t yStride, uint32_t n, float eps, uint32_t T,
+                      cudaStream_t stream) {
+    rmsNormBf16Kernel<<<T, 256, 0, stream>>>(x, xStride, w, (__nv_bfloat16 *)y, yStride, n, eps);
+    DL_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace dl
+
+DL_EXPORT int dl_gemm_q40_tc(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride,
+                             uint32_t T, void *out, uint32_t outStride, int numSms, cudaStream_t stream, int pdl) {
+    return dl::gemmQ40Tc(epi, qs, scales, d, n, act, actStride, T, out, outStride, numSms, stream, pdl != 0);
+}
+
+DL_EXPORT int dl_rmsnorm_bf16(const float *x, uint32_t xStride, const float *w, void *y, uint32_t yStride, uint32_t n, float eps,
+                              uint32_t T, cudaStream_t stream) {
+    return dl::launchRmsNormBf16(x, xStride, w, y, yStride, n, eps, T, stream);
+}

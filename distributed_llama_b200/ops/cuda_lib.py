@@ -51,6 +51,10 @@ def lib() -> C.CDLL:
     L.dl_dequant_device_q40.restype = i32
     L.dl_gemv_q40.argtypes = [i32, i32, i32, vp, vp, u32, u32, vp, u32, vp, f32, vp, u32, i32, vp, i32, i32]
     L.dl_gemv_q40.restype = i32
+    L.dl_gemm_q40_tc.argtypes = [i32, vp, vp, u32, u32, vp, u32, u32, vp, u32, i32, vp, i32]
+    L.dl_gemm_q40_tc.restype = i32
+    L.dl_rmsnorm_bf16.argtypes = [vp, u32, vp, vp, u32, u32, f32, u32, vp]
+    L.dl_rmsnorm_bf16.restype = i32
     L.dl_engine_create.argtypes = [C.POINTER(EngineConfig)]
     L.dl_engine_create.restype = vp
     L.dl_engine_destroy.argtypes = [vp]
@@ -91,3 +95,4 @@ def stream_ptr() -> int:
 
 PRO_RMSNORM, PRO_PLAIN = 0, 1
 EPI_STORE, EPI_RESIDUAL, EPI_SWIGLU = 0, 1, 2
+GEPI_STORE_F32, GEPI_RESIDUAL, GEPI_SWIGLU_BF16, GEPI_STORE_BF16 = 0, 1, 2, 3

@@ -53,3 +53,23 @@ def gemv_q40(w: DeviceQ40, x: torch.Tensor, *, pro: int, epi: int, out: torch.Te
                                   norm_w.data_ptr() if norm_w is not None else None, eps, out.data_ptr(), out.stride(0),
                                   num_sms, cl.stream_ptr(), 1 if pdl else 0, {"auto": 0, "ldg": 1, "tma": 2}[impl]), "gemv_q40")
     return out
+
+
+def gemm_q40_tc(w: DeviceQ40, act: torch.Tensor, *, epi: int, out: torch.Tensor, num_sms: int = 0, pdl: bool = False) -> torch.Tensor:
+    """tcgen05 prefill GEMM. act: bf16 [T, n] (T <= 256); out: [T, d] f32 (STORE/RESIDUAL), bf16 [T, d/2] (SWIGLU) or bf16 [T, d]."""
+    assert act.dtype == torch.bfloat16 and act.is_cuda and act.stride(1) == 1
+    if num_sms == 0:
+        num_sms = torch.cuda.get_device_properties(act.device).multi_processor_count
+    cl.check(cl.lib().dl_gemm_q40_tc(epi, w.qs.data_ptr(), w.scales.data_ptr(), w.d, w.n, act.data_ptr(), act.stride(0), act.shape[0],
+                                     out.data_ptr(), out.stride(0), num_sms, cl.stream_ptr(), 1 if pdl else 0), "gemm_q40_tc")
+    return out
+
+
+def rmsnorm_bf16(x: torch.Tensor, w: Optional[torch.Tensor], eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: f32 [T, n] -> bf16 [T, n] = w * x * rsqrt(mean(x^2) + eps); w=None converts only."""
+    T, n = x.shape
+    if out is None:
+        out = torch.empty(T, n, dtype=torch.bfloat16, device=x.device)
+    cl.check(cl.lib().dl_rmsnorm_bf16(x.data_ptr(), x.stride(0), w.data_ptr() if w is not None else None, out.data_ptr(), out.stride(0),
+                                      n, eps, T, cl.stream_ptr()), "rmsnorm_bf16")
+    return out
