@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(128) attnDecodeKernel(AttnArgs a) {
             num += w * __ldcg(pIn + (size_t)s * (HD + 2) + threadIdx.x);
             den += w * __ldcg(pIn + (size_t)s * (HD + 2) + HD + 1);
         }
-        a.out[(size_t)t * a.outStride + (size_t)h * HD + threadIdx.x] = num / den;
+        if (a.outBf16) a.outBf16[(size_t)t * a.outStride + (size_t)h * HD + threadIdx.x] = __float2bfloat16_rn(num / den);
+        else a.out[(size_t)t * a.outStride + (size_t)h * HD + threadIdx.x] = num / den;
     }
 }
 

@@ -49,6 +49,13 @@ struct GlobalPtrs {
     // MoE scratch
     int *expertIdx;              // [maxBatch][nActive]
     float *expertWeight;         // [maxBatch][nActive]
+    // prefill (tensor-core GEMM path) buffers, maxPrefill tokens
+    uint32_t maxPrefill;
+    int *pTokens, *pPos;         // [maxPrefill]
+    float *px, *pqkv;            // [maxPrefill][dim | qkvDim] f32
+    void *pxn, *pzb, *phb;       // bf16 [maxPrefill][dim | qDim | ff]
+    float *pAttnPartial;         // [maxPrefill][nHeads][hd+2]
+    unsigned int *pAttnCounters; // [maxPrefill][nHeads]
     // fused arg-max scratch
     float *argVal;               // [numSms]
     int *argIdx;                 // [numSms]
@@ -186,6 +193,44 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
     return 0;
 }
 
+// Prompt chunk of T <= maxPrefill tokens on the tensor-core path. Logits (optional) are produced for the last token.
+static int enginePrefill(Engine &e, uint32_t T, int wantLogits, cudaStream_t stream) {
+    const EngineConfig &c = e.cfg;
+    const GlobalPtrs &g = e.g;
+    const bool pdl = false;   // plain stream order between the heterogeneous kernels of this path
+    const uint32_t qDim = c.nHeads * c.headDim, kvDim = c.nKvHeads * c.headDim, qkvDim = qDim + 2 * kvDim;
+    if (T < 1 || T > g.maxPrefill || T > 256) return -11;
+    if (e.comm.nRanks > 1) return -12;   // tensor-parallel prefill runs on the GEMV path (fused all-reduce)
+    DL_TRY(launchEmbedding(g.embedding, g.pTokens, g.px, c.dim, c.dim, g.vocabFull, (int)T, stream));
+    for (uint32_t l = 0; l < c.nLayers; l++) {
+        const LayerPtrs &L = e.layers[l];
+        DL_TRY(launchRmsNormBf16(g.px, c.dim, L.norm0, g.pxn, c.dim, c.dim, c.eps, T, stream));
+        DL_TRY(gemmQ40Tc(GEPI_STORE_F32_, L.qkvQs, L.qkvSc, qkvDim, c.dim, g.pxn, c.dim, T, g.pqkv, qkvDim, c.numSms, stream, pdl));
+        RopeKvArgs r{};
+        r.qkv = g.pqkv; r.qkvStride = qkvDim; r.pos = g.pPos; r.rope = g.rope; r.qNorm = L.qNorm; r.kNorm = L.kNorm;
+        r.eps = c.eps; r.nHeads = c.nHeads; r.nKvHeads = c.nKvHeads; r.headDim = c.headDim; r.seqLen = c.seqLen;
+        r.kCache = (__nv_bfloat16 *)L.kCache; r.vCache = (__nv_bfloat16 *)L.vCache;
+        DL_TRY(launchRopeKv(r, (int)T, stream, pdl));
+        AttnArgs t{};
+        t.qkv = g.pqkv; t.qkvStride = qkvDim; t.pos = g.pPos; t.kCache = r.kCache; t.vCache = r.vCache;
+        t.nHeads = c.nHeads; t.nKvHeads = c.nKvHeads; t.headDim = c.headDim; t.seqLen = c.seqLen; t.nSplits = 1;
+        t.partial = g.pAttnPartial; t.counters = g.pAttnCounters; t.out = nullptr; t.outStride = qDim; t.outBf16 = (__nv_bfloat16 *)g.pzb;
+        DL_TRY(launchAttnDecode(t, (int)T, stream, pdl));
+        DL_TRY(gemmQ40Tc(GEPI_RESIDUAL_, L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, pdl));
+        DL_TRY(launchRmsNormBf16(g.px, c.dim, L.norm1, g.pxn, c.dim, c.dim, c.eps, T, stream));
+        DL_TRY(gemmQ40Tc(GEPI_SWIGLU_BF16_, L.w13Qs, L.w13Sc, 2 * c.ffDim, c.dim, g.pxn, c.dim, T, g.phb, c.ffDim, c.numSms, stream, pdl));
+        DL_TRY(gemmQ40Tc(GEPI_RESIDUAL_, L.w2Qs, L.w2Sc, c.dim, c.ffDim, g.phb, c.ffDim, T, g.px, c.dim, c.numSms, stream, pdl));
+    }
+    if (wantLogits) {
+        GemvArgs a{};
+        a.qs = (const uint32_t *)g.wclsQs; a.scales = (const __half *)g.wclsSc; a.d = c.vocab; a.n = c.dim;
+        a.normW = g.finalNorm; a.eps = c.eps; a.inStride = c.dim; a.outStride = c.vocab; a.out = g.logits;
+        a.in = g.px + (size_t)(T - 1) * c.dim;
+        DL_TRY(gemvSel(e, PRO_RMSNORM_, EPI_STORE_, 1, a, c.numSms, stream, false));
+    }
+    return 0;
+}
+
 }  // namespace dl
 
 using dl::Engine;
@@ -241,6 +286,10 @@ DL_EXPORT uint32_t dl_engine_num_sms(void *h) { return ((Engine *)h)->cfg.numSms
 
 DL_EXPORT int dl_engine_forward(void *h, int nb, int logitsMode, int greedyAdvance, cudaStream_t stream) {
     return dl::engineForward(*(Engine *)h, nb, logitsMode, greedyAdvance != 0, stream);
+}
+
+DL_EXPORT int dl_engine_prefill(void *h, uint32_t T, int wantLogits, cudaStream_t stream) {
+    return dl::enginePrefill(*(Engine *)h, T, wantLogits, stream);
 }
 
 // Captures one greedy decode step (forward of 1 token + argmax + position advance) into a graph.

@@ -72,6 +72,7 @@ struct AttnArgs {
     unsigned int *counters;
     float *out;
     uint32_t outStride;
+    __nv_bfloat16 *outBf16;   // if set, the result is written here (bf16) instead of `out`
 };
 int launchAttnDecode(const AttnArgs &a, int nb, cudaStream_t stream, bool pdl);
 
@@ -95,5 +96,12 @@ int launchEmbedding(const float *table, const int *tokens, float *x, uint32_t di
                     cudaStream_t stream);
 int launchArgmaxAdvance(const float *logits, uint32_t vocab, int *tokenOut, int *pos, int *history, uint32_t historyCap,
                         cudaStream_t stream, bool pdl);
+
+// tcgen05 prefill GEMM (gemm_q40_tc.cu)
+enum { GEPI_STORE_F32_ = 0, GEPI_RESIDUAL_ = 1, GEPI_SWIGLU_BF16_ = 2, GEPI_STORE_BF16_ = 3 };
+int gemmQ40Tc(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T,
+              void *out, uint32_t outStride, int numSms, cudaStream_t stream, bool pdl);
+int launchRmsNormBf16(const float *x, uint32_t xStride, const float *w, void *y, uint32_t yStride, uint32_t n, float eps, uint32_t T,
+                      cudaStream_t stream);
 
 }  // namespace dl

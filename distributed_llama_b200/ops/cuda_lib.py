@@ -30,6 +30,8 @@ class GlobalPtrs(C.Structure):
     _fields_ = [("embedding", vp), ("finalNorm", vp), ("wclsQs", vp), ("wclsSc", vp), ("rope", vp), ("vocabFull", u32),
                 ("tokens", vp), ("pos", vp), ("x", vp), ("qkv", vp), ("z", vp), ("h", vp), ("logits", vp),
                 ("attnPartial", vp), ("attnCounters", vp), ("history", vp), ("expertIdx", vp), ("expertWeight", vp),
+                ("maxPrefill", u32), ("pTokens", vp), ("pPos", vp), ("px", vp), ("pqkv", vp), ("pxn", vp), ("pzb", vp), ("phb", vp),
+                ("pAttnPartial", vp), ("pAttnCounters", vp),
                 ("argVal", vp), ("argIdx", vp), ("argCounter", vp)]
 
 
@@ -75,6 +77,8 @@ def lib() -> C.CDLL:
     L.dl_engine_num_sms.restype = u32
     L.dl_engine_forward.argtypes = [vp, i32, i32, i32, vp]
     L.dl_engine_forward.restype = i32
+    L.dl_engine_prefill.argtypes = [vp, u32, i32, vp]
+    L.dl_engine_prefill.restype = i32
     L.dl_engine_capture_decode.argtypes = [vp]
     L.dl_engine_capture_decode.restype = i32
     L.dl_engine_decode_graph.argtypes = [vp, i32, vp]

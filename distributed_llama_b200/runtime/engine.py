@@ -23,7 +23,7 @@ def _p(t: Optional[torch.Tensor]):
 
 class Engine:
     def __init__(self, weights: DeviceWeights, max_batch: int = 8, n_splits: int = 0, use_pdl: bool = True,
-                 seq_len: Optional[int] = None, comm=None):
+                 seq_len: Optional[int] = None, comm=None, max_prefill: int = 256):
         self.w = w = weights
         h = w.header
         dev = w.embedding.device
@@ -53,6 +53,17 @@ class Engine:
         self.v_cache = [torch.zeros(w.n_kv_heads, self.seq_len, hd, dtype=torch.bfloat16, device=dev) for _ in range(h.n_layers)]
         self.expert_idx = torch.zeros(max_batch * max(1, h.n_active_experts), dtype=torch.int32, device=dev)
         self.expert_weight = torch.zeros(max_batch * max(1, h.n_active_experts), **f32)
+        self.max_prefill = mp = min(max_prefill, 256)
+        bf16 = dict(dtype=torch.bfloat16, device=dev)
+        self.p_tokens = torch.zeros(mp, dtype=torch.int32, device=dev)
+        self.p_pos = torch.zeros(mp, dtype=torch.int32, device=dev)
+        self.p_x = torch.zeros(mp, h.dim, **f32)
+        self.p_qkv = torch.zeros(mp, self.qkv_dim, **f32)
+        self.p_xn = torch.zeros(mp, h.dim, **bf16)
+        self.p_zb = torch.zeros(mp, q_dim, **bf16)
+        self.p_hb = torch.zeros(mp, w.ff_dim, **bf16)
+        self.p_attn_partial = torch.zeros(mp * w.n_heads * (hd + 2), **f32)
+        self.p_attn_counters = torch.zeros(mp * w.n_heads, dtype=torch.int32, device=dev)
         self.arg_val = torch.zeros(256, **f32)
         self.arg_idx = torch.zeros(256, dtype=torch.int32, device=dev)
         self.arg_counter = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -74,6 +85,9 @@ class Engine:
                            pos=_p(self.pos), x=_p(self.x), qkv=_p(self.qkv), z=_p(self.z), h=_p(self.h),
                            logits=_p(self.logits), attnPartial=_p(self.attn_partial), attnCounters=_p(self.attn_counters),
                            history=_p(self.history), expertIdx=_p(self.expert_idx), expertWeight=_p(self.expert_weight),
+                           maxPrefill=mp, pTokens=_p(self.p_tokens), pPos=_p(self.p_pos), px=_p(self.p_x), pqkv=_p(self.p_qkv),
+                           pxn=_p(self.p_xn), pzb=_p(self.p_zb), phb=_p(self.p_hb), pAttnPartial=_p(self.p_attn_partial),
+                           pAttnCounters=_p(self.p_attn_counters),
                            argVal=_p(self.arg_val), argIdx=_p(self.arg_idx), argCounter=_p(self.arg_counter))
         cl.check(self._lib.dl_engine_set_globals(self._h, C.byref(gp)), "engine_set_globals")
         self.comm = comm
@@ -82,6 +96,8 @@ class Engine:
             comm.alloc_arena(arena_layout(comm.world_size, max_batch, h.dim, h.vocab_size))
             cp = comm.comm_ptrs(max_batch * h.dim)
             cl.check(self._lib.dl_engine_set_comm(self._h, C.byref(cp)), "engine_set_comm")
+        self.use_tc_prefill = True
+        self.tc_min_tokens = 9          # shorter chunks stay on the GEMV path
         self._graph_ready = False
         self._stage_tok = torch.zeros(max_batch, dtype=torch.int32).pin_memory()
         self._stage_pos = torch.zeros(max_batch, dtype=torch.int32).pin_memory()
@@ -123,16 +139,27 @@ class Engine:
         cl.check(self._lib.dl_engine_forward(self._h, n, logits_mode, 1 if greedy_advance else 0, cl.stream_ptr()), "engine_forward")
 
     def prefill(self, tokens: Sequence[int], start_pos: int = 0, want_logits: bool = True) -> Optional[torch.Tensor]:
-        """Feeds a prompt chunk by chunk; returns the logits row of the last token (device tensor view)."""
+        """Feeds a prompt; returns the logits row of its last token (device tensor). Single GPU: chunks of up to 256 tokens
+        on the tcgen05 GEMM path. Tensor parallel: chunks of up to max_batch tokens on the GEMV path (fused all-reduce)."""
         tokens = list(tokens)
+        if start_pos + len(tokens) > self.seq_len:
+            raise ValueError("position beyond the context length")
+        tc_path = (self.comm is None or self.comm.world_size == 1) and self.w.header.n_experts == 0 and self.use_tc_prefill
         i = 0
         while i < len(tokens):
             rem = len(tokens) - i
-            n = 1
-            while n * 2 <= min(rem, self.max_batch):
-                n *= 2
-            last = i + n == len(tokens)
-            self.forward_batch(tokens[i:i + n], start_pos + i, logits_mode=1 if (last and want_logits) else 0)
+            if tc_path and rem >= self.tc_min_tokens:
+                n = min(rem, self.max_prefill)
+                last = i + n == len(tokens)
+                self.p_tokens[:n].copy_(torch.tensor(tokens[i:i + n], dtype=torch.int32))
+                self.p_pos[:n].copy_(torch.arange(start_pos + i, start_pos + i + n, dtype=torch.int32))
+                cl.check(self._lib.dl_engine_prefill(self._h, n, 1 if (last and want_logits) else 0, cl.stream_ptr()), "engine_prefill")
+            else:
+                n = 1
+                while n * 2 <= min(rem, self.max_batch):
+                    n *= 2
+                last = i + n == len(tokens)
+                self.forward_batch(tokens[i:i + n], start_pos + i, logits_mode=1 if (last and want_logits) else 0)
             i += n
         return self._full_logits(self.logits[0]) if want_logits else None
 
