@@ -1,0 +1,155 @@
+"""Root/worker application runtime (reference: runInferenceApp / runWorkerApp, src/app.cpp:232-365).
+
+Process model on the B200 box: one process per GPU. Rank 0 is the *root* (tokenizer, sampler, user I/O), ranks >= 1 are
+*workers*: they hold their tensor-parallel weight slices and mirror every forward the root issues. Control flows as the
+reference's 8-byte LlmControlPacket {position, batchSize} (src/app.hpp:46-49) — here extended with an opcode and broadcast
+with torch.distributed; batchSize == 0 is the stop signal. All activation traffic happens inside the kernels over NVLink.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import host
+from ..api import InferenceSession
+from .args import AppArgs
+
+OP_STOP, OP_PREFILL, OP_STEP_LOGITS, OP_STEP_GREEDY = 0, 1, 2, 3
+
+
+def world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_distributed_from_env():
+    """Initialises torch.distributed when launched by torchrun (RANK/WORLD_SIZE set). Returns (comm or None)."""
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws <= 1:
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        return None
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from ..parallel.comm import Communicator
+    return Communicator()
+
+
+class RootInference:
+    """Root-side handle (reference RootLlmInference, src/app.cpp:168-208): every call first tells the workers what to run."""
+
+    def __init__(self, sess: InferenceSession, comm):
+        self.sess = sess
+        self.comm = comm
+        self.eng = sess.engine
+        self.header = sess.header
+        self.eval_ms = 0.0
+        self._ctl = torch.zeros(4, dtype=torch.int64, device=sess.device) if comm is not None else None
+
+    def _send(self, op: int, pos: int, tokens: Sequence[int]):
+        if self.comm is None:
+            return
+        import torch.distributed as dist
+        n = len(tokens)
+        self._ctl[0], self._ctl[1], self._ctl[2] = op, pos, n
+        dist.broadcast(self._ctl, 0)
+        if n:
+            t = torch.tensor(list(tokens), dtype=torch.int64, device=self.sess.device)
+            dist.broadcast(t, 0)
+
+    def prefill(self, tokens: Sequence[int], pos: int) -> None:
+        if tokens:
+            self._send(OP_PREFILL, pos, tokens)
+            self.eng.prefill(tokens, pos, want_logits=False)
+
+    def forward_logits(self, token: int, pos: int) -> torch.Tensor:
+        self._send(OP_STEP_LOGITS, pos, [token])
+        return self.eng.step(token, pos)
+
+    def forward_greedy(self, token: int, pos: int) -> int:
+        self._send(OP_STEP_GREEDY, pos, [token])
+        self.eng._set_inputs([token], pos)
+        self.eng.run_decode_step()
+        return int(self.eng.tokens[0].item())
+
+    def finish(self):
+        self._send(OP_STOP, 0, [])
+
+
+def worker_loop(sess: InferenceSession, comm) -> None:
+    """Worker main loop (reference runWorkerApp, src/app.cpp:306-365): mirror the root's forwards until the stop packet."""
+    import torch.distributed as dist
+    ctl = torch.zeros(4, dtype=torch.int64, device=sess.device)
+    eng = sess.engine
+    while True:
+        dist.broadcast(ctl, 0)
+        op, pos, n = int(ctl[0]), int(ctl[1]), int(ctl[2])
+        if op == OP_STOP:
+            print("🛑 Stop signal")
+            return
+        t = torch.zeros(n, dtype=torch.int64, device=sess.device)
+        dist.broadcast(t, 0)
+        toks = t.tolist()
+        if op == OP_PREFILL:
+            eng.prefill(toks, pos, want_logits=False)
+        elif op == OP_STEP_LOGITS:
+            eng.step(toks[0], pos)
+        elif op == OP_STEP_GREEDY:
+            eng._set_inputs(toks, pos)
+            eng.run_decode_step()
+
+
+@dataclass
+class AppContext:
+    args: AppArgs
+    sess: InferenceSession
+    inference: RootInference
+    tokenizer: object
+    sampler: object
+    header: object
+
+
+def run_inference_app(args: AppArgs, handler: Callable[[AppContext], None]) -> None:
+    if args.model is None:
+        raise RuntimeError("Model is required")
+    if args.tokenizer is None:
+        raise RuntimeError("Tokenizer is required")
+    comm = init_distributed_from_env()
+    rank = comm.rank if comm else 0
+    H = host()
+    header = H.load_model_header(args.model, args.max_seq_len)
+    n_nodes = comm.world_size if comm else 1
+    if header.weight_type == H.F_Q40 and args.buffer_float_type != "q80":
+        raise RuntimeError("This version supports only Q40 weights with Q80 sync type")
+    sess = InferenceSession(args.model, args.tokenizer, max_seq_len=args.max_seq_len, temperature=args.temperature,
+                            topp=args.topp, seed=args.seed, comm=comm)
+    if rank != 0:
+        worker_loop(sess, comm)
+        return
+    tok = sess.tokenizer
+    if args.info:
+        if tok.vocab_size != header.vocab_size:
+            print(f"Tokenizer vocab size ({tok.vocab_size}) does not match the model vocab size ({header.vocab_size})")
+        print(tok.describe(), end="")
+        print(header.describe(), end="")
+        req = H.required_device_bytes(header, n_nodes, 2)
+        print(f"📀 RequiredMemory: {req // (1024 * 1024)} MB")
+        name = torch.cuda.get_device_name(sess.device)
+        print(f"🧠 GPU: {name} x{n_nodes} (sm_100a kernels; tensor parallel over NVLink peer memory)")
+        print("💿 Weights loaded")
+    inf = RootInference(sess, comm)
+    ctx = AppContext(args=args, sess=sess, inference=inf, tokenizer=tok, sampler=sess.sampler, header=header)
+    try:
+        handler(ctx)
+    finally:
+        inf.finish()
