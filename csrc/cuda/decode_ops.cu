@@ -400,6 +400,95 @@ __global__ void __launch_bounds__(128) attnFusedKernel(AttnFusedArgs a) {
     }
 }
 
+// ---- MoE router: rmsnorm + gate GEMV (f32) + softmax + top-k + renormalise ---------------------------------------
+// Reference ops: MATMUL(block_moe_gate) + SOFTMAX + MOE_GATE (src/llm.cpp:432-449, nn-cpu-ops.cpp:900-916,1462-1492).
+// grid (nExperts/8, nb), block 256: every warp produces one expert logit; the last CTA of a token selects the top-k
+// (lowest index wins ties) and writes the routing weights softmax(top-k logits).
+__global__ void __launch_bounds__(256) moeRouterKernel(RouterArgs a) {
+    pdlLaunchDependents();
+    pdlWait();
+    extern __shared__ float sy[];      // [dim] normalised activations
+    __shared__ float red[8];
+    __shared__ bool sLast;
+    const uint32_t t = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4 *x4 = reinterpret_cast<const float4 *>(a.x + (size_t)t * a.dim);
+    float ss = 0.f;
+    for (uint32_t i = threadIdx.x; i < a.dim / 4; i += 256) {
+        const float4 v = x4[i];
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warpSum(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < 8; i++) tot += red[i];
+    const float inv = rsqrtf(tot / (float)a.dim + a.eps);
+    for (uint32_t i = threadIdx.x; i < a.dim / 4; i += 256) {
+        const float4 v = x4[i];
+        const float4 w = reinterpret_cast<const float4 *>(a.normW)[i];
+        reinterpret_cast<float4 *>(sy)[i] = make_float4(w.x * (v.x * inv), w.y * (v.y * inv), w.z * (v.z * inv), w.w * (v.w * inv));
+    }
+    __syncthreads();
+    const uint32_t e = blockIdx.x * 8 + warp;
+    if (e < a.nExperts) {
+        const float4 *g4 = reinterpret_cast<const float4 *>(a.gate + (size_t)e * a.dim);
+        float d = 0.f;
+        for (uint32_t i = lane; i < a.dim / 4; i += 32) {
+            const float4 g = g4[i];
+            const float4 y = reinterpret_cast<const float4 *>(sy)[i];
+            d += g.x * y.x + g.y * y.y + g.z * y.z + g.w * y.w;
+        }
+        d = warpSum(d);
+        if (lane == 0) a.logits[(size_t)t * a.nExperts + e] = d;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&a.counter[t], 1u);
+        sLast = prev == gridDim.x - 1;
+        if (sLast) a.counter[t] = 0;
+    }
+    __syncthreads();
+    if (!sLast || warp != 0) return;
+    __threadfence();
+    // single warp: iterative arg-max over <= 256 experts (8 per lane)
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t idx = lane + 32 * j;
+        v[j] = idx < a.nExperts ? __ldcg(a.logits + (size_t)t * a.nExperts + idx) : -INFINITY;
+    }
+    float selV[8];
+    int selI[8];
+    for (uint32_t kk = 0; kk < a.k; kk++) {
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (v[j] > best) { best = v[j]; bi = lane + 32 * j; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        selV[kk] = best;
+        selI[kk] = bi;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (lane + 32 * j == bi) v[j] = -INFINITY;
+    }
+    if (lane == 0) {
+        float sum = 0.f;
+        for (uint32_t kk = 0; kk < a.k; kk++) sum += __expf(selV[kk] - selV[0]);
+        for (uint32_t kk = 0; kk < a.k; kk++) {
+            a.expertIdx[t * a.k + kk] = selI[kk];
+            a.expertWeight[t * a.k + kk] = __expf(selV[kk] - selV[0]) / sum;
+        }
+    }
+}
+
 // ---- greedy sampling -----------------------------------------------------------------------------------------
 // One CTA scans the logits row, writes the arg-max token for the next step and advances the position.
 __global__ void __launch_bounds__(1024) argmaxAdvanceKernel(const float *__restrict__ logits, uint32_t vocab, int *tokenOut,
@@ -473,6 +562,22 @@ int launchAttnDecode(const AttnArgs &a, int nb, cudaStream_t stream, bool pdl) {
     if (a.headDim == 128) return launchPdl(attnDecodeKernel<128>, grid, dim3(128), stream, pdl, a);
     if (a.headDim == 64) return launchPdl(attnDecodeKernel<64>, grid, dim3(128), stream, pdl, a);
     return -1;
+}
+
+int launchMoeRouter(const RouterArgs &a, int nb, cudaStream_t stream, bool pdl) {
+    if (a.nExperts > 256 || a.k > 8 || a.dim % 4) return -1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((a.nExperts + 7) / 8, nb);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = a.dim * sizeof(float);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, moeRouterKernel, a));
+    return 0;
 }
 
 int launchAttnFused(const AttnFusedArgs &a, cudaStream_t stream, bool pdl) {

@@ -22,6 +22,7 @@ struct EngineConfig {   // mirrored by ctypes in distributed_llama_b200/ops/cuda
     uint32_t numSms;
     float eps;
     uint32_t usePdl;
+    uint32_t moeFirstExpert, moeNumLocal;   // experts held by this rank (expert parallelism); TP mode: 0, nExperts
 };
 
 struct LayerPtrs {
@@ -49,6 +50,10 @@ struct GlobalPtrs {
     // MoE scratch
     int *expertIdx;              // [maxBatch][nActive]
     float *expertWeight;         // [maxBatch][nActive]
+    float *routerLogits;         // [maxBatch][nExperts]
+    unsigned int *routerCounter; // [maxBatch]
+    float *moeScratch;           // [nActive][dim]
+    unsigned int *moeCounters;   // [256]
     // prefill (tensor-core GEMM path) buffers, maxPrefill tokens
     uint32_t maxPrefill;
     int *pTokens, *pPos;         // [maxPrefill]
@@ -150,6 +155,33 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
         a.in = e.g.z; a.inStride = qDim; a.out = e.g.x; a.outStride = c.dim; a.trace = nextTrace();
         if (e.comm.nRanks > 1) fillAr(e, a.ar, 0);
         DL_TRY(gemvSel(e, PRO_PLAIN_, EPI_RESIDUAL_, nb, a, c.numSms, stream, pdl));
+        if (c.nExperts > 0) {
+            // 5-7. mixture of experts: router -> k x (W1|W3 -> silu*up) -> k x W2, weighted sum, residual (+ all-reduce)
+            if (nb != 1) return -13;
+            RouterArgs ro{};
+            ro.x = e.g.x; ro.normW = L.norm1; ro.gate = L.moeGate; ro.eps = c.eps; ro.dim = c.dim; ro.nExperts = c.nExperts;
+            ro.k = c.nActiveExperts; ro.logits = e.g.routerLogits; ro.counter = e.g.routerCounter; ro.expertIdx = e.g.expertIdx;
+            ro.expertWeight = e.g.expertWeight;
+            nextTrace();
+            DL_TRY(launchMoeRouter(ro, nb, stream, pdl));
+            const uint32_t perSlot = c.numSms / c.nActiveExperts > 0 ? c.numSms / c.nActiveExperts : 1;
+            a = GemvArgs{};
+            a.qs = (const uint32_t *)L.w13Qs; a.scales = (const __half *)L.w13Sc; a.d = 2 * c.ffDim; a.n = c.dim;
+            a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm1; a.eps = c.eps; a.out = e.g.h; a.outStride = c.ffDim; a.trace = nextTrace();
+            a.moeCtasPerSlot = perSlot; a.kActive = c.nActiveExperts; a.expertIdx = e.g.expertIdx; a.outSlotStride = c.ffDim;
+            a.expertQsStride = (uint64_t)2 * c.ffDim * (c.dim / 8); a.expertScaleStride = (uint64_t)2 * c.ffDim * (c.dim / 32);
+            a.moeFirstExpert = c.moeFirstExpert; a.moeNumLocal = c.moeNumLocal;
+            { const int r = gemvQ40Tma(PRO_RMSNORM_, EPI_SWIGLU_, 1, a, c.numSms, stream, pdl); if (r != 0) return r == 1 ? -31 : r; }
+            a = GemvArgs{};
+            a.qs = (const uint32_t *)L.w2Qs; a.scales = (const __half *)L.w2Sc; a.d = c.dim; a.n = c.ffDim;
+            a.in = e.g.h; a.inStride = c.ffDim; a.inSlotStride = c.ffDim; a.out = e.g.x; a.outStride = c.dim; a.trace = nextTrace();
+            a.moeCtasPerSlot = perSlot; a.kActive = c.nActiveExperts; a.expertIdx = e.g.expertIdx; a.expertWeight = e.g.expertWeight;
+            a.expertQsStride = (uint64_t)c.dim * (c.ffDim / 8); a.expertScaleStride = (uint64_t)c.dim * (c.ffDim / 32);
+            a.moeFirstExpert = c.moeFirstExpert; a.moeNumLocal = c.moeNumLocal; a.moeScratch = e.g.moeScratch; a.moeCounters = e.g.moeCounters;
+            if (e.comm.nRanks > 1) fillAr(e, a.ar, 1);
+            { const int r = gemvQ40Tma(PRO_PLAIN_, EPI_MOE_DOWN_, 1, a, c.numSms, stream, pdl); if (r != 0) return r == 1 ? -32 : r; }
+            continue;
+        }
         // 5. rmsnorm -> q80 -> W1|W3 -> silu*up
         a = GemvArgs{};
         a.qs = (const uint32_t *)L.w13Qs; a.scales = (const __half *)L.w13Sc; a.d = 2 * c.ffDim; a.n = c.dim;

@@ -16,7 +16,7 @@
 namespace dl {
 
 enum { PRO_RMSNORM = 0, PRO_PLAIN = 1 };
-enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_ARGMAX = 3 };
+enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_ARGMAX = 3, EPI_MOE_DOWN = 4 };
 
 constexpr int kConsumerWarps = 16;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
@@ -101,10 +101,14 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
     const uint32_t nseg = (nblk + 31) / 32;
     const uint32_t rowQsBytes = nblk * 16, rowScBytes = nblk * 2;
 
-    // ---- tile (pair aligned, like the fallback kernel) ----
+    // ---- tile (pair aligned, like the fallback kernel); MoE launches carry one tile grid per routing slot ----
+    const bool moe = a.moeCtasPerSlot != 0;
+    const uint32_t nTiles = moe ? a.moeCtasPerSlot : gridDim.x;
+    const uint32_t tileIdx = moe ? blockIdx.x % a.moeCtasPerSlot : blockIdx.x;
+    const uint32_t slot = moe ? blockIdx.x / a.moeCtasPerSlot : 0;
     const uint32_t nPairs = a.d / 2;
-    const uint32_t pairBegin = (uint32_t)(((uint64_t)blockIdx.x * nPairs) / gridDim.x);
-    const uint32_t pairEnd = (uint32_t)(((uint64_t)(blockIdx.x + 1) * nPairs) / gridDim.x);
+    const uint32_t pairBegin = (uint32_t)(((uint64_t)tileIdx * nPairs) / nTiles);
+    const uint32_t pairEnd = (uint32_t)(((uint64_t)(tileIdx + 1) * nPairs) / nTiles);
     const uint32_t rowBase = pairBegin * 2;
     const uint32_t tileRows = (pairEnd - pairBegin) * 2;
     const uint32_t SR = geo.stageRows;
@@ -132,16 +136,15 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
     }
     __syncthreads();
 
-    const bool moe = a.expertIdx != nullptr;
-
     if (warp == kConsumerWarps) {
         // =============================== producer ===============================
         if (lane == 0) {
             const uint8_t *qsBase = reinterpret_cast<const uint8_t *>(a.qs);
             const uint8_t *scBase = reinterpret_cast<const uint8_t *>(a.scales);
             if (moe) {
-                pdlWait();
-                const int e = a.expertIdx[a.slot];
+                pdlWait();   // the expert choice is produced by the router kernel
+                const uint32_t e = (uint32_t)a.expertIdx[slot] - a.moeFirstExpert;
+                if (e >= a.moeNumLocal) return;   // expert lives on another rank (expert parallelism): nothing to stream
                 qsBase += (uint64_t)e * a.expertQsStride * 4;
                 scBase += (uint64_t)e * a.expertScaleStride * 2;
             }
@@ -169,13 +172,15 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
     }
     pdlWait();
     traceStamp(a.trace, 1);
+    const bool active = !moe || ((uint32_t)a.expertIdx[slot] - a.moeFirstExpert) < a.moeNumLocal;
+    const float *inBase = a.in + (size_t)slot * a.inSlotStride;
 
     // ---- prologue: (rmsnorm) + q80 quantisation into the dp4a plane layout ----
-    {
+    if (active) {
         const uint32_t nVec = a.n / 4;
 #pragma unroll 1
         for (int t = 0; t < NB; t++) {
-            const float4 *x4 = reinterpret_cast<const float4 *>(a.in + (size_t)t * a.inStride);
+            const float4 *x4 = reinterpret_cast<const float4 *>(inBase + (size_t)t * a.inStride);
             float inv = 1.f;
             if (PRO == PRO_RMSNORM) {
                 float ss = 0.f;
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
     traceStamp(a.trace, 2);
 
     // ---- main loop over ring stages ----
-    for (uint32_t f = 0; f < nFills; f++) {
+    for (uint32_t f = 0; active && f < nFills; f++) {
         const uint32_t st = f % geo.nStages;
         const uint32_t r0 = f * SR;
         const uint32_t rows = min(SR, tileRows - r0);
@@ -301,32 +306,56 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
     consumerBarrier();
 
     // ---- epilogue ----
+    auto rowSum = [&](uint32_t r, uint32_t t) {
+        float v = 0.f;
+        for (uint32_t sg = 0; sg < nseg; sg++) v += partial[((size_t)r * nseg + sg) * NB + t];
+        return v;
+    };
     if (EPI == EPI_SWIGLU) {
         const uint32_t tilePairs = tileRows / 2;
+        float *outBase = a.out + (size_t)slot * a.outSlotStride;
         for (uint32_t i = tid; i < tilePairs * NB; i += kConsumerThreads) {
             const uint32_t p = i / NB, t = i - p * NB;
-            float g = 0.f, up = 0.f;
-            for (uint32_t sg = 0; sg < nseg; sg++) {
-                g += partial[((size_t)(2 * p) * nseg + sg) * NB + t];
-                up += partial[((size_t)(2 * p + 1) * nseg + sg) * NB + t];
-            }
-            a.out[(size_t)t * a.outStride + pairBegin + p] = siluf(g) * up;
+            outBase[(size_t)t * a.outStride + pairBegin + p] = active ? siluf(rowSum(2 * p, t)) * rowSum(2 * p + 1, t) : 0.f;
         }
-    } else {
-        float best = -INFINITY;
-        int bestIdx = 0x7fffffff;
-        if (EPI == EPI_RESIDUAL && a.ar.nRanks > 1) {
+    } else if (EPI == EPI_RESIDUAL || EPI == EPI_MOE_DOWN) {
+        __shared__ bool sLastSlot;
+        if (EPI == EPI_MOE_DOWN) {
+            // every routing slot leaves its weighted product in the scratch; the last slot CTA of a row tile sums the
+            // slots in fixed order (deterministic) and carries on with the residual add / all-reduce
+            const float wgt = active ? a.expertWeight[slot] : 0.f;
+            for (uint32_t i = tid; i < tileRows; i += kConsumerThreads)
+                a.moeScratch[(size_t)slot * a.d + rowBase + i] = active ? rowSum(i, 0) * wgt : 0.f;
+            __threadfence();
+            consumerBarrier();
+            if (tid == 0) {
+                const unsigned int prev = atomicAdd(&a.moeCounters[tileIdx], 1u);
+                sLastSlot = prev == a.kActive - 1;
+                if (sLastSlot) a.moeCounters[tileIdx] = 0;
+            }
+            consumerBarrier();
+            if (!sLastSlot) { traceStamp(a.trace, 3); return; }
+            __threadfence();
+        }
+        auto value = [&](uint32_t r, uint32_t t) {
+            if (EPI == EPI_MOE_DOWN) {
+                float v = 0.f;
+                for (uint32_t j = 0; j < a.kActive; j++) v += __ldcg(a.moeScratch + (size_t)j * a.d + rowBase + r);
+                return v;
+            }
+            return rowSum(r, t);
+        };
+        if (a.ar.nRanks > 1) {
             // ---- fused one-shot all-reduce over NVLink peer memory + residual add -------------------------------
-            // Every rank computed the partial product of the same row tile in the CTA with the same index. Push the
-            // partial rows into slot[myRank] of *every* rank (peer stores), raise one flag per destination, wait for
-            // the flags of all sources, then sum the slots in rank order (bit-identical result on every rank).
-            // LL protocol: every 8-byte word carries (partial value, valid flag); receivers poll the words and clear them.
+            // Every rank computed the partial product of the same row tile in the CTA with the same index. LL protocol:
+            // every 8-byte word carries (partial value, valid flag); the partial rows are stored into slot[myRank] of
+            // *every* rank, receivers poll the words of all sources, sum them in rank order (bit-identical result on
+            // every rank) and clear them for the all-reduce after next (the slots are double buffered by parity).
             const ArArgs &ar = a.ar;
             const size_t slotBase = (size_t)(ar.parity * ar.nRanks + ar.rank) * ar.slotStride;
             for (uint32_t i = tid; i < tileRows * NB; i += kConsumerThreads) {
                 const uint32_t r = i / NB, t = i - r * NB;
-                float v = 0.f;
-                for (uint32_t sg = 0; sg < nseg; sg++) v += partial[((size_t)r * nseg + sg) * NB + t];
+                const float v = value(r, t);
                 const size_t off = slotBase + (size_t)t * ar.dim + rowBase + r;
 #pragma unroll 1
                 for (uint32_t p = 0; p < ar.nRanks; p++) stLL(ar.slots[(ar.rank + p) % ar.nRanks] + off, __float_as_uint(v), 1u);
@@ -339,24 +368,25 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
                     uint64_t *w = mine + (size_t)(ar.parity * ar.nRanks + sr) * ar.slotStride + (size_t)t * ar.dim + rowBase + r;
                     uint2 v = ldLL(w);
                     while (v.y == 0u) v = ldLL(w);
-                    sum += __uint_as_float(v.x);              // fixed rank order: bit-identical on every rank
-                    stLL(w, 0u, 0u);                          // re-arm for the all-reduce after next (double buffered)
+                    sum += __uint_as_float(v.x);
+                    stLL(w, 0u, 0u);
                 }
                 a.out[(size_t)t * a.outStride + rowBase + r] += sum;
             }
-        } else
+        } else {
+            for (uint32_t i = tid; i < tileRows * NB; i += kConsumerThreads) {
+                const uint32_t r = i / NB, t = i - r * NB;
+                a.out[(size_t)t * a.outStride + rowBase + r] += value(r, t);
+            }
+        }
+    } else {
+        float best = -INFINITY;
+        int bestIdx = 0x7fffffff;
         for (uint32_t i = tid; i < tileRows * NB; i += kConsumerThreads) {
             const uint32_t r = i / NB, t = i - r * NB;
-            float v = 0.f;
-            for (uint32_t sg = 0; sg < nseg; sg++) v += partial[((size_t)r * nseg + sg) * NB + t];
-            float *o = a.out + (size_t)t * a.outStride + rowBase + r;
-            if (EPI == EPI_RESIDUAL) {
-                if (a.expertWeight) v *= a.expertWeight[t * a.kActive + a.slot];
-                *o += v;
-            } else {
-                *o = v;
-                if (EPI == EPI_ARGMAX && v > best) { best = v; bestIdx = (int)(a.rowOffsetGlobal + rowBase + r); }   // rows ascend per thread
-            }
+            const float v = rowSum(r, t);
+            a.out[(size_t)t * a.outStride + rowBase + r] = v;
+            if (EPI == EPI_ARGMAX && v > best) { best = v; bestIdx = (int)(a.rowOffsetGlobal + rowBase + r); }   // rows ascend per thread
         }
         if (EPI == EPI_ARGMAX) {
             // greedy sampling fused into the logits kernel: CTA-level arg-max, then the last CTA to finish reduces
@@ -470,9 +500,15 @@ int gemvQ40Tma(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t st
     if (a.d % 2 || a.n % 128) return 1;   // bulk copies need 16-byte aligned row starts for the fp16 scale rows
     const uint32_t nblk = a.n / 32, nseg = (nblk + 31) / 32;
     const uint32_t nPairs = a.d / 2;
-    const int grid = (int)(nPairs < (uint32_t)numSms ? nPairs : (uint32_t)numSms);
+    int grid = (int)(nPairs < (uint32_t)numSms ? nPairs : (uint32_t)numSms);
+    uint32_t tilesPerMatrix = (uint32_t)grid;
+    if (a.moeCtasPerSlot) {
+        if (nb != 1) return -4;
+        tilesPerMatrix = a.moeCtasPerSlot;
+        grid = (int)(a.moeCtasPerSlot * a.kActive);
+    }
     TmaGemvGeom geo{};
-    geo.maxTileRows = 2 * ((nPairs + grid - 1) / grid);
+    geo.maxTileRows = 2 * ((nPairs + tilesPerMatrix - 1) / tilesPerMatrix);
     const uint32_t rowBytes = nblk * 18;
     // a stage should hold >= 16 steps (one per consumer warp) so the per-stage barrier traffic is amortised
     uint32_t sr = (64 + nseg - 1) / nseg;
@@ -502,6 +538,7 @@ int gemvQ40Tma(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t st
     DL_TMA_NB(PRO_PLAIN, EPI_STORE)
     DL_TMA_CASE(PRO_PLAIN, EPI_SWIGLU, 1)
     DL_TMA_CASE(PRO_RMSNORM, EPI_ARGMAX, 1)
+    DL_TMA_CASE(PRO_PLAIN, EPI_MOE_DOWN, 1)
 #undef DL_TMA_NB
 #undef DL_TMA_CASE
     return -3;

@@ -5,7 +5,7 @@
 namespace dl {
 
 enum { PRO_RMSNORM_ = 0, PRO_PLAIN_ = 1 };
-enum { EPI_STORE_ = 0, EPI_RESIDUAL_ = 1, EPI_SWIGLU_ = 2, EPI_ARGMAX_ = 3 };
+enum { EPI_STORE_ = 0, EPI_RESIDUAL_ = 1, EPI_SWIGLU_ = 2, EPI_ARGMAX_ = 3, EPI_MOE_DOWN_ = 4 };
 
 // In-kernel one-shot all-reduce over NVLink peer memory (see the EPI_RESIDUAL epilogue of gemv_q40_tma.cu).
 constexpr int kMaxRanks = 8;
@@ -39,6 +39,12 @@ struct GemvArgs {
     uint32_t historyCap;
     uint32_t rowOffsetGlobal; // added to row indices (vocab slice offset under tensor parallelism)
     uint64_t *trace;          // optional 4-slot timeline record for this launch
+    // Mixture-of-experts launches (moeCtasPerSlot > 0, nb == 1): CTA b works for routing slot b / moeCtasPerSlot on the row
+    // tile b % moeCtasPerSlot of expert expertIdx[slot]; experts outside [moeFirstExpert, +moeNumLocal) are skipped (EP).
+    uint32_t moeCtasPerSlot, moeFirstExpert, moeNumLocal;
+    uint32_t inSlotStride, outSlotStride;   // floats between slots of the input (w2) / output (w13) buffers
+    float *moeScratch;          // [kActive][d] weighted per-slot products (EPI_MOE_DOWN)
+    unsigned int *moeCounters;  // [moeCtasPerSlot], zero-initialised, self-resetting
     ArArgs ar;                // ar.nRanks > 1: EPI_RESIDUAL sums the partial products of all ranks before the residual add
 };
 int gemvQ40(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl);      // per-thread loads (fallback)
@@ -91,6 +97,19 @@ struct AttnFusedArgs {
     uint64_t *trace;
 };
 int launchAttnFused(const AttnFusedArgs &a, cudaStream_t stream, bool pdl);
+
+struct RouterArgs {
+    const float *x;            // [nb][dim] residual stream
+    const float *normW;        // [dim]
+    const float *gate;         // [nExperts][dim] f32
+    float eps;
+    uint32_t dim, nExperts, k;
+    float *logits;             // [nb][nExperts] scratch
+    unsigned int *counter;     // [nb], zero-initialised, self-resetting
+    int *expertIdx;            // [nb][k]
+    float *expertWeight;       // [nb][k]
+};
+int launchMoeRouter(const RouterArgs &a, int nb, cudaStream_t stream, bool pdl);
 
 int launchEmbedding(const float *table, const int *tokens, float *x, uint32_t dim, uint32_t xStride, uint32_t vocab, int nb,
                     cudaStream_t stream);

@@ -55,6 +55,9 @@ class DeviceWeights:
     rope: torch.Tensor
     layers: List[LayerWeights] = field(default_factory=list)
     bytes_uploaded: int = 0
+    first_expert: int = 0        # experts held by this rank (expert parallelism), all of them in TP mode
+    n_local_experts: int = 0
+    moe_mode: str = "tp"
 
 
 def _interleave_perm(head_dim: int) -> np.ndarray:
@@ -89,32 +92,41 @@ class _Uploader:
         return torch.from_numpy(np.ascontiguousarray(x)).to(self.device)
 
 
-def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="cuda") -> DeviceWeights:
+def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="cuda", moe_mode: str = "auto") -> DeviceWeights:
+    """moe_mode (Qwen3-MoE only): "tp" slices every expert over the ranks like the reference (src/llm.cpp:454-486);
+    "ep" gives each rank nExperts/nRanks whole experts (expert parallelism: the expert FFN streams full-width matrices and the
+    combine is the same in-kernel all-reduce); "auto" picks ep when the TP slice would be narrower than 128 columns."""
     h = mf.header
     if h.weight_type != quants.F_Q40:
         raise NotImplementedError("the CUDA engine currently runs q40 weight files (as the reference's GPU/CPU fast path)")
     H = host()
-    if h.n_heads % n_ranks or h.n_kv_heads % n_ranks or h.ff_dim % n_ranks or h.vocab_size % n_ranks:
+    if moe_mode == "auto":
+        moe_mode = "ep" if (h.n_experts > 0 and n_ranks > 1 and (h.ff_dim // n_ranks) % 128 != 0 and h.n_experts % n_ranks == 0) else "tp"
+    ep = h.n_experts > 0 and moe_mode == "ep" and n_ranks > 1
+    if ep and h.n_experts % n_ranks:
+        raise ValueError("nExperts must be divisible by the number of ranks for expert parallelism")
+    if h.n_heads % n_ranks or h.n_kv_heads % n_ranks or (not ep and h.ff_dim % n_ranks) or h.vocab_size % n_ranks:
         raise ValueError("nHeads, nKvHeads, ffDim and vocabSize must be divisible by the number of ranks")
     hd = h.head_dim
     nh, nkv = h.n_heads // n_ranks, h.n_kv_heads // n_ranks
-    q0, kv0, ff0, v0 = nh * hd, nkv * hd, h.ff_dim // n_ranks, h.vocab_size // n_ranks
+    q0, kv0, ff0, v0 = nh * hd, nkv * hd, (h.ff_dim if ep else h.ff_dim // n_ranks), h.vocab_size // n_ranks
     if (q0 % 32) or (ff0 % 32):
         raise ValueError("column slices must cover whole 32-element quant blocks")
     neox = h.rope_type == ROPE_FALCON
     up = _Uploader(mf, device)
     dim = h.dim
 
-    def row_sliced(name, layer, expert, dst: DeviceQ40, rows_local, dst_stride=1, dst_off=0, head_dim=0):
+    def row_sliced(name, layer, expert, dst: DeviceQ40, rows_local, dst_stride=1, dst_off=0, head_dim=0, slice_rank=None):
         e = mf.entry(name, layer, expert)
-        raw = up.rows(e, rank * rows_local, rows_local)
+        raw = up.rows(e, (rank if slice_rank is None else slice_rank) * rows_local, rows_local)
         repack_q40(raw, rows_local, e.n, dst, dst_row_stride=dst_stride, dst_row_offset=dst_off, head_dim=head_dim)
 
-    def col_sliced(name, layer, expert, dst: DeviceQ40, cols_local, dst_off=0):
+    def col_sliced(name, layer, expert, dst: DeviceQ40, cols_local, dst_off=0, slice_rank=None):
         e = mf.entry(name, layer, expert)
         raw = up.rows(e, 0, e.d)
         repack_q40(raw, e.d, cols_local, dst, src_row_pitch=quants.tensor_bytes(e.type, e.n),
-                   src_col_byte_offset=quants.tensor_bytes(e.type, rank * cols_local), dst_row_offset=dst_off)
+                   src_col_byte_offset=quants.tensor_bytes(e.type, (rank if slice_rank is None else slice_rank) * cols_local),
+                   dst_row_offset=dst_off)
 
     W = DeviceWeights(header=h, rank=rank, n_ranks=n_ranks, n_heads=nh, n_kv_heads=nkv, ff_dim=ff0, vocab=v0,
                       embedding=up.f32(mf.entry("embedding")), final_norm=up.f32(mf.entry("final_norm")),
@@ -123,6 +135,9 @@ def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="
     row_sliced("final_matmul_logits", 0, 0, W.wcls, v0)
     perm = torch.from_numpy(_interleave_perm(hd)).to(device) if neox else None
     n_exp = max(h.n_experts, 1)
+    first_exp, n_local = (rank * (h.n_experts // n_ranks), h.n_experts // n_ranks) if ep else (0, n_exp)
+    W.first_expert, W.n_local_experts, W.moe_mode = first_exp, (n_local if h.n_experts > 0 else 0), ("ep" if ep else "tp")
+    esr = 0 if ep else None      # expert tensors: whole matrices under EP
     for l in range(h.n_layers):
         qkv = DeviceQ40.empty(q0 + 2 * kv0, dim, device)
         row_sliced("block_matmul_q", l, 0, qkv, q0, head_dim=hd if neox else 0)
@@ -130,12 +145,13 @@ def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="
         row_sliced("block_matmul_v", l, 0, qkv, kv0, dst_off=q0 + kv0)
         wo = DeviceQ40.empty(dim, q0, device)
         col_sliced("block_matmul_wo", l, 0, wo, q0)
-        w13 = DeviceQ40.empty(2 * ff0, dim, device, lead=n_exp)
-        w2 = DeviceQ40.empty(dim, ff0, device, lead=n_exp)
-        for e in range(n_exp):
-            row_sliced("block_matmul_w1", l, e, w13, ff0, dst_stride=2, dst_off=e * 2 * ff0)
-            row_sliced("block_matmul_w3", l, e, w13, ff0, dst_stride=2, dst_off=e * 2 * ff0 + 1)
-            col_sliced("block_matmul_w2", l, e, w2, ff0, dst_off=e * dim)
+        w13 = DeviceQ40.empty(2 * ff0, dim, device, lead=n_local)
+        w2 = DeviceQ40.empty(dim, ff0, device, lead=n_local)
+        for le in range(n_local):
+            e = first_exp + le
+            row_sliced("block_matmul_w1", l, e, w13, ff0, dst_stride=2, dst_off=le * 2 * ff0, slice_rank=esr)
+            row_sliced("block_matmul_w3", l, e, w13, ff0, dst_stride=2, dst_off=le * 2 * ff0 + 1, slice_rank=esr)
+            col_sliced("block_matmul_w2", l, e, w2, ff0, dst_off=le * dim, slice_rank=esr)
         L = LayerWeights(qkv=qkv, wo=wo, w13=w13, w2=w2, norm0=up.f32(mf.entry("block_norm_0", l)),
                          norm1=up.f32(mf.entry("block_norm_1", l)))
         if h.qk_norm:

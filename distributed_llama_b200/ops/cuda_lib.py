@@ -18,7 +18,7 @@ u32, u64, i32, f32, vp = C.c_uint32, C.c_uint64, C.c_int, C.c_float, C.c_void_p
 class EngineConfig(C.Structure):
     _fields_ = [(n, u32) for n in ("dim", "nLayers", "nHeads", "nKvHeads", "headDim", "ffDim", "vocab", "seqLen",
                                    "nExperts", "nActiveExperts", "maxBatch", "nSplits", "rank", "nRanks", "numSms")] + \
-               [("eps", f32), ("usePdl", u32)]
+               [("eps", f32), ("usePdl", u32), ("moeFirstExpert", u32), ("moeNumLocal", u32)]
 
 
 class LayerPtrs(C.Structure):
@@ -30,6 +30,7 @@ class GlobalPtrs(C.Structure):
     _fields_ = [("embedding", vp), ("finalNorm", vp), ("wclsQs", vp), ("wclsSc", vp), ("rope", vp), ("vocabFull", u32),
                 ("tokens", vp), ("pos", vp), ("x", vp), ("qkv", vp), ("z", vp), ("h", vp), ("logits", vp),
                 ("attnPartial", vp), ("attnCounters", vp), ("history", vp), ("expertIdx", vp), ("expertWeight", vp),
+                ("routerLogits", vp), ("routerCounter", vp), ("moeScratch", vp), ("moeCounters", vp),
                 ("maxPrefill", u32), ("pTokens", vp), ("pPos", vp), ("px", vp), ("pqkv", vp), ("pxn", vp), ("pzb", vp), ("phb", vp),
                 ("pAttnPartial", vp), ("pAttnCounters", vp),
                 ("argVal", vp), ("argIdx", vp), ("argCounter", vp)]

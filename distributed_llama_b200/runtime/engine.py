@@ -29,6 +29,8 @@ class Engine:
         dev = w.embedding.device
         self.device = dev
         self.seq_len = seq_len or h.seq_len
+        if h.n_experts > 0:
+            max_batch = 1          # the MoE kernels route one token per launch
         self.max_batch = max_batch
         props = torch.cuda.get_device_properties(dev)
         self.num_sms = props.multi_processor_count
@@ -44,7 +46,11 @@ class Engine:
         self.x = torch.zeros(max_batch, h.dim, **f32)
         self.qkv = torch.zeros(max_batch, self.qkv_dim, **f32)
         self.z = torch.zeros(max_batch, q_dim, **f32)
-        self.h = torch.zeros(max_batch, w.ff_dim, **f32)
+        self.h = torch.zeros(max(max_batch, h.n_active_experts, 1), w.ff_dim, **f32)
+        self.router_logits = torch.zeros(max_batch * max(1, h.n_experts), **f32)
+        self.router_counter = torch.zeros(max_batch, dtype=torch.int32, device=dev)
+        self.moe_scratch = torch.zeros(max(1, h.n_active_experts) * h.dim, **f32)
+        self.moe_counters = torch.zeros(256, dtype=torch.int32, device=dev)
         self.logits = torch.zeros(max_batch, w.vocab, **f32)
         self.attn_partial = torch.zeros(max_batch * w.n_heads * n_splits * (hd + 2), **f32)
         self.attn_counters = torch.zeros(max_batch * w.n_heads, dtype=torch.int32, device=dev)
@@ -71,7 +77,8 @@ class Engine:
         cfg = cl.EngineConfig(dim=h.dim, nLayers=h.n_layers, nHeads=w.n_heads, nKvHeads=w.n_kv_heads, headDim=hd,
                               ffDim=w.ff_dim, vocab=w.vocab, seqLen=self.seq_len, nExperts=h.n_experts,
                               nActiveExperts=h.n_active_experts, maxBatch=max_batch, nSplits=n_splits, rank=w.rank,
-                              nRanks=w.n_ranks, numSms=self.num_sms, eps=h.norm_epsilon, usePdl=1 if use_pdl else 0)
+                              nRanks=w.n_ranks, numSms=self.num_sms, eps=h.norm_epsilon, usePdl=1 if use_pdl else 0,
+                              moeFirstExpert=w.first_expert, moeNumLocal=w.n_local_experts)
         self._lib = cl.lib()
         self._h = self._lib.dl_engine_create(C.byref(cfg))
         for l, L in enumerate(w.layers):
@@ -85,6 +92,8 @@ class Engine:
                            pos=_p(self.pos), x=_p(self.x), qkv=_p(self.qkv), z=_p(self.z), h=_p(self.h),
                            logits=_p(self.logits), attnPartial=_p(self.attn_partial), attnCounters=_p(self.attn_counters),
                            history=_p(self.history), expertIdx=_p(self.expert_idx), expertWeight=_p(self.expert_weight),
+                           routerLogits=_p(self.router_logits), routerCounter=_p(self.router_counter),
+                           moeScratch=_p(self.moe_scratch), moeCounters=_p(self.moe_counters),
                            maxPrefill=mp, pTokens=_p(self.p_tokens), pPos=_p(self.p_pos), px=_p(self.p_x), pqkv=_p(self.p_qkv),
                            pxn=_p(self.p_xn), pzb=_p(self.p_zb), phb=_p(self.p_hb), pAttnPartial=_p(self.p_attn_partial),
                            pAttnCounters=_p(self.p_attn_counters),
@@ -194,6 +203,8 @@ class Engine:
 
     @property
     def launches_per_decode_step(self) -> int:
+        if self.w.header.n_experts > 0:
+            return self.w.header.n_layers * 6 + 2
         return self.w.header.n_layers * 5 + 2   # embedding + 5 fused kernels per layer + logits/arg-max
 
     def capture_decode(self):
