@@ -31,7 +31,7 @@ class GenerationStats:
 class InferenceSession:
     def __init__(self, model_path: str, tokenizer_path: Optional[str] = None, max_seq_len: int = 0,
                  temperature: float = 0.0, topp: float = 0.9, seed: int = 12345, device: Optional[str] = None,
-                 max_batch: int = 8, use_pdl: bool = True, comm=None):
+                 max_batch: int = 8, use_pdl: bool = True, comm=None, moe_mode: str = "auto"):
         from .models.loader import load_device_weights
         from .runtime.engine import Engine
 
@@ -43,7 +43,7 @@ class InferenceSession:
         if device is None:
             device = f"cuda:{torch.cuda.current_device()}"
         self.device = torch.device(device)
-        self.weights = load_device_weights(self.model_file, rank, n_ranks, self.device)
+        self.weights = load_device_weights(self.model_file, rank, n_ranks, self.device, moe_mode=moe_mode)
         self.engine = Engine(self.weights, max_batch=max_batch, use_pdl=use_pdl, comm=comm)
         H = host()
         self.tokenizer = H.Tokenizer(tokenizer_path) if tokenizer_path else None

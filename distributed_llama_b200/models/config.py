@@ -90,7 +90,7 @@ PRESETS: Dict[str, ModelConfig] = {
     "tiny-qwen3": ModelConfig("tiny-qwen3", ARCH_QWEN3, 256, 512, 2, 4, 2, 512, 256, head_dim=128,
                               rope_theta=1000000, norm_epsilon=6),
     "tiny-qwen3-moe": ModelConfig("tiny-qwen3-moe", ARCH_QWEN3_MOE, 256, 512, 2, 4, 2, 512, 256, head_dim=128,
-                                  n_experts=8, n_active_experts=2, moe_hidden_dim=128, rope_theta=1000000,
+                                  n_experts=8, n_active_experts=2, moe_hidden_dim=256, rope_theta=1000000,
                                   norm_epsilon=6),
 }
 

@@ -17,6 +17,7 @@ from distributed_llama_b200.runtime import Engine
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "tiny-llama31"
+    moe_mode = sys.argv[2] if len(sys.argv) > 2 else "auto"
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -26,7 +27,7 @@ def main():
         write_synthetic_model(path, get_config(name), seed=11)
     dist.barrier()
     mf = ModelFile(path)
-    eng = Engine(load_device_weights(mf, comm.rank, comm.world_size), comm=comm)
+    eng = Engine(load_device_weights(mf, comm.rank, comm.world_size, moe_mode=moe_mode), comm=comm)
     prompt = [3, 17, 250, 9, 44, 101, 7, 300, 12, 5, 77]
     # logits through the step API (all-gathered across ranks)
     lg = []
@@ -34,10 +35,10 @@ def main():
         lg.append(eng.step(t, i).clone())
     lg = torch.stack(lg)
     # greedy decode on the device (cross-rank arg-max inside the logits kernel), graph replay
-    eng2 = Engine(load_device_weights(mf, comm.rank, comm.world_size), comm=comm)
+    eng2 = Engine(load_device_weights(mf, comm.rank, comm.world_size, moe_mode=moe_mode), comm=comm)
     eng2.prefill(prompt[:-1], 0, want_logits=False)
     toks_graph = eng2.decode_greedy(prompt[-1], len(prompt) - 1, 32, use_graph=True)
-    eng3 = Engine(load_device_weights(mf, comm.rank, comm.world_size), comm=comm)
+    eng3 = Engine(load_device_weights(mf, comm.rank, comm.world_size, moe_mode=moe_mode), comm=comm)
     eng3.prefill(prompt[:-1], 0, want_logits=False)
     toks_eager = eng3.decode_greedy(prompt[-1], len(prompt) - 1, 32, use_graph=False)
     # every rank must have produced the same tokens
@@ -58,7 +59,7 @@ def main():
         e1 = (lg - ref_lg).abs().max().item()
         e2 = (lg - olg).abs().max().item()
         n_agree = sum(a == b for a, b in zip(toks_graph, ref_toks))
-        print(f"tp={comm.world_size} max|tp - tp1|={e1:.4g} max|tp - oracle|={e2:.4g} greedy agree {n_agree}/32 "
+        print(f"moe_mode={eng.w.moe_mode} tp={comm.world_size} max|tp - tp1|={e1:.4g} max|tp - oracle|={e2:.4g} greedy agree {n_agree}/32 "
               f"graph==eager {toks_graph == toks_eager} ranks agree {same_across_ranks}")
         ok = e1 < 0.05 and e2 < 0.08 and toks_graph == toks_eager and same_across_ranks and n_agree >= 8
         print("TP_CHECK", "PASS" if ok else "FAIL")
