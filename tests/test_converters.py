@@ -1,0 +1,75 @@
+"""Converter parity: a tiny random HF Llama / Qwen3 checkpoint -> convert_hf -> `.m` -> PyTorch oracle must reproduce the
+HuggingFace model's logits (validates tensor order, q/k re-ordering, rope conventions, QK-norm, header mapping)."""
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load_tool(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _hf_model(kind, tmp_path):
+    transformers = pytest.importorskip("transformers")
+    torch.manual_seed(0)
+    if kind == "llama":
+        cfg = transformers.LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                                       num_key_value_heads=2, vocab_size=300, max_position_embeddings=128, rms_norm_eps=1e-5,
+                                       rope_theta=10000.0, tie_word_embeddings=False, hidden_act="silu")
+        model = transformers.LlamaForCausalLM(cfg)
+    else:
+        cfg = transformers.Qwen3Config(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                                       num_key_value_heads=2, head_dim=64, vocab_size=300, max_position_embeddings=128,
+                                       rms_norm_eps=1e-6, rope_theta=1000000.0, tie_word_embeddings=True, hidden_act="silu")
+        model = transformers.Qwen3ForCausalLM(cfg)
+    model = model.float().eval()
+    d = tmp_path / kind
+    model.save_pretrained(str(d), safe_serialization=True)
+    return model, str(d)
+
+
+@pytest.mark.parametrize("kind", ["llama", "qwen3"])
+def test_convert_hf_matches_transformers(kind, tmp_path):
+    from distributed_llama_b200.formats import ModelFile
+    from distributed_llama_b200.models.reference import OracleModel
+    model, folder = _hf_model(kind, tmp_path)
+    conv = _load_tool("convert_hf")
+    out = str(tmp_path / f"{kind}.m")
+    conv.convert(folder, "f32", out)
+    mf = ModelFile(out)
+    assert mf.header.dim == 128 and mf.header.n_layers == 2 and mf.header.vocab_size == 300
+    toks = [5, 17, 250, 9, 44, 101, 7, 299, 12]
+    with torch.no_grad():
+        ref = model(torch.tensor([toks])).logits[0]
+    got = OracleModel(mf).forward(toks, 0)
+    assert (got - ref).abs().max().item() < 2e-3
+    # q40 file: same geometry, coarser numerics
+    out40 = str(tmp_path / f"{kind}_q40.m")
+    conv.convert(folder, "q40", out40)
+    got40 = OracleModel(ModelFile(out40)).forward(toks, 0)
+    assert (got40 - ref).abs().max().item() < 0.35 * ref.abs().max().item()
+
+
+def test_llama3_tokenizer_converter(tmp_path):
+    import base64
+    from distributed_llama_b200 import host
+    conv = _load_tool("convert_tokenizer_llama3")
+    src = tmp_path / "tokenizer.model"
+    pieces = [bytes([b]) for b in range(256)] + [b"he", b"ll", b"hell", b"hello", b" w", b" wo"]
+    src.write_text("".join(f"{base64.b64encode(p).decode()} {i}\n" for i, p in enumerate(pieces)))
+    out = str(tmp_path / "l3.t")
+    conv.convert(str(src), out)
+    tk = host().Tokenizer(out)
+    assert tk.bos_id == len(pieces) and tk.vocab_size == len(pieces) + 256 and tk.piece(tk.eos_ids[1]) == b"<|eot_id|>"
+    ids = tk.encode("hello<|eot_id|>", True, True)
+    assert [tk.piece(i) for i in ids] == [b"<|begin_of_text|>", b"hello", b"<|eot_id|>"]
