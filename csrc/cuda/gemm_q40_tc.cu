@@ -15,6 +15,7 @@
 //                                in bf16 in global memory, HBM traffic stays at 4.5 bits/weight.
 // Persistent CTAs loop over 128-row tiles; all synchronisation is mbarrier based (no __syncthreads in the main loop).
 #include <cuda.h>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -37,6 +38,8 @@ struct GemmArgs {
     void *out;
     uint32_t outStride;   // elements between tokens
     uint32_t stages, tmemCols;
+    uint32_t rawStages;    // TMA-staged variant: depth of the raw q40 ring (2 or 3)
+    uint32_t debugFlags;   // bit0: skip the proxy fence, bit1: skip the A-tile stores (timing experiments only)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -173,6 +176,12 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcKernel(const __grid_co
             const bool fOk = f < a.d;
             for (uint32_t c0 = 0; c0 < nTile; c0 += 16) {
                 uint32_t r[16];
+                float resid[16];
+                if (EPI == GEPI_RESIDUAL) {   // issue all residual loads of the 16-column group before any store (no serialised RMW chain)
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        resid[j] = (c0 + j < a.T && fOk) ? __ldcg(reinterpret_cast<const float *>(a.out) + (size_t)(c0 + j) * a.outStride + f) : 0.f;
+                }
                 tmemLoad16(tmemBase + ((q * 32u) << 16) + acc * nTile + c0, r);
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcKernel(const __grid_co
                             reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(siluf(v) * other);
                     } else if (tok < a.T && fOk) {
                         if (EPI == GEPI_STORE_F32) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v;
-                        if (EPI == GEPI_RESIDUAL) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] += v;
+                        if (EPI == GEPI_RESIDUAL) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v + resid[j];
                         if (EPI == GEPI_STORE_BF16) reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + f] = __float2bfloat16_rn(v);
                     }
                 }
@@ -268,6 +277,230 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcKernel(const __grid_co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant with the raw q40 stream staged by TMA (n % 256 == 0): warp 3 issues two tensor-map loads per 256-wide K chunk
+// ([128 rows x 128 B] nibbles, SWIZZLE_128B so the 16-byte reads of 8 consecutive rows hit different banks, and
+// [128 rows x 16 B] scales) into a 3-deep ring; the dequant warps read the chunk from shared memory. ~54 KB of weight
+// bytes are in flight per SM instead of the 16 KB the register-prefetching variant above can hold.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kGmRawStagesMax = 3;
+constexpr int kGmRawK = 256;
+constexpr int kGmRawQsBytes = kGmBlockM * 128;               // 16 KB
+constexpr int kGmRawStageBytes = kGmRawQsBytes + kGmBlockM * 16;   // + 2 KB scales
+
+template <int EPI>
+__global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid_constant__ CUtensorMap tmapB,
+                                                                    const __grid_constant__ CUtensorMap tmapQ,
+                                                                    const __grid_constant__ CUtensorMap tmapS, GemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t smemRaw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nTile = a.nTile;
+    const uint32_t bTileBytes = nTile * 128;
+    const uint32_t stageBytes = kGmATileBytes + bTileBytes;
+    uint8_t *rawBase = smem + (size_t)a.stages * stageBytes;          // [kGmRawStages][18 KB], 1024-aligned (stageBytes % 1024 == 0)
+    uint64_t *fullBar = reinterpret_cast<uint64_t *>(rawBase + (size_t)a.rawStages * kGmRawStageBytes);
+    uint64_t *emptyBar = fullBar + kGmMaxStages;
+    uint64_t *tmemFull = emptyBar + kGmMaxStages;
+    uint64_t *tmemEmpty = tmemFull + 2;
+    uint64_t *rawFull = tmemEmpty + 2;
+    uint64_t *rawEmpty = rawFull + kGmRawStagesMax;
+    uint32_t *tmemBasePtr = reinterpret_cast<uint32_t *>(rawEmpty + kGmRawStagesMax);
+
+    const uint32_t nkb = a.n / kGmBlockK;
+    const uint32_t nkq = (a.n + kGmRawK - 1) / kGmRawK;
+    const uint32_t nTilesM = (a.d + kGmBlockM - 1) / kGmBlockM;
+
+    pdlLaunchDependents();
+    if (tid == 0) {
+        for (uint32_t s = 0; s < a.stages; s++) {
+            gmBarInit(&fullBar[s], 1 + 2);   // activation TMA + the two dequant warps that own this k-slice
+            gmBarInit(&emptyBar[s], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            gmBarInit(&tmemFull[i], 1);
+            gmBarInit(&tmemEmpty[i], 4);
+        }
+        for (uint32_t i = 0; i < a.rawStages; i++) {
+            gmBarInit(&rawFull[i], 1);
+            gmBarInit(&rawEmpty[i], kGmDeqWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sAddr(tmemBasePtr)), "r"(a.tmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    const uint32_t tmemBase = *tmemBasePtr;
+
+    if (warp == 3) {
+        // ===================== raw weight producer (weights are constants: no dependency wait) =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x) {
+                for (uint32_t kq = 0; kq < nkq; kq++, it++) {
+                    const uint32_t rs = it % a.rawStages, ph = (it / a.rawStages) & 1;
+                    gmBarWait(&rawEmpty[rs], ph ^ 1);
+                    uint8_t *dst = rawBase + (size_t)rs * kGmRawStageBytes;
+                    gmBarExpectTx(&rawFull[rs], kGmRawStageBytes);
+                    tmaLoad2d(dst, &tmapQ, kq * 128, tile * kGmBlockM, &rawFull[rs]);                 // nibbles: 128 B per row
+                    tmaLoad2d(dst + kGmRawQsBytes, &tmapS, kq * 16, tile * kGmBlockM, &rawFull[rs]);   // scales: 16 B per row
+                }
+            }
+        }
+    } else if (warp == 0) {
+        // ===================== activation producer =====================
+        pdlWait();
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x) {
+                for (uint32_t kb = 0; kb < nkb; kb++, it++) {
+                    const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                    gmBarWait(&emptyBar[s], ph ^ 1);
+                    gmBarExpectTx(&fullBar[s], bTileBytes);
+                    tmaLoad2d(smem + (size_t)s * stageBytes + kGmATileBytes, &tmapB, kb * kGmBlockK, 0, &fullBar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((nTile >> 3) << 17) | ((uint32_t)(kGmBlockM >> 4) << 24);
+        uint32_t it = 0, tcount = 0;
+        for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x, tcount++) {
+            const uint32_t acc = tcount & 1, accPh = (tcount >> 1) & 1;
+            gmBarWait(&tmemEmpty[acc], accPh ^ 1);
+            tcFenceAfter();
+            const uint32_t tmemD = tmemBase + acc * nTile;
+            for (uint32_t kb = 0; kb < nkb; kb++, it++) {
+                const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                gmBarWait(&fullBar[s], ph);
+                tcFenceAfter();
+                if (lane == 0) {
+                    const uint32_t aAddr = sAddr(smem + (size_t)s * stageBytes);
+                    const uint64_t descA = makeSmemDesc(aAddr);
+                    const uint64_t descB = makeSmemDesc(aAddr + kGmATileBytes);
+#pragma unroll
+                    for (uint32_t k = 0; k < kGmBlockK / 16; k++) umma(tmemD, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    ummaCommit(&emptyBar[s]);
+                    if (kb == nkb - 1) ummaCommit(&tmemFull[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== epilogue =====================
+        pdlWait();   // the residual stream is read-modify-written
+        const uint32_t q = warp - 4;
+        uint32_t tcount = 0;
+        for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x, tcount++) {
+            const uint32_t acc = tcount & 1, accPh = (tcount >> 1) & 1;
+            gmBarWait(&tmemFull[acc], accPh);
+            tcFenceAfter();
+            const uint32_t f = tile * kGmBlockM + q * 32 + lane;
+            const bool fOk = f < a.d;
+            for (uint32_t c0 = 0; c0 < nTile; c0 += 16) {
+                uint32_t r[16];
+                float resid[16];
+                if (EPI == GEPI_RESIDUAL) {   // issue all residual loads of the 16-column group before any store (no serialised RMW chain)
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        resid[j] = (c0 + j < a.T && fOk) ? __ldcg(reinterpret_cast<const float *>(a.out) + (size_t)(c0 + j) * a.outStride + f) : 0.f;
+                }
+                tmemLoad16(tmemBase + ((q * 32u) << 16) + acc * nTile + c0, r);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint32_t tok = c0 + j;
+                    const float v = __uint_as_float(r[j]);
+                    if (EPI == GEPI_SWIGLU_BF16) {
+                        const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+                        if (tok < a.T && fOk && !(lane & 1))
+                            reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(siluf(v) * other);
+                    } else if (tok < a.T && fOk) {
+                        if (EPI == GEPI_STORE_F32) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v;
+                        if (EPI == GEPI_RESIDUAL) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v + resid[j];
+                        if (EPI == GEPI_STORE_BF16) reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + f] = __float2bfloat16_rn(v);
+                    }
+                }
+            }
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) gmBarArrive(&tmemEmpty[acc]);
+        }
+    } else if (warp >= 8) {
+        // ===================== dequant: shared-memory q40 chunk -> bf16 UMMA tile =====================
+        // Four groups of two warps; group g converts the g-th 64-wide k-slice of every 256-wide raw chunk, so four A tiles
+        // are being converted concurrently and the load -> convert -> store -> proxy-fence latency of one slice overlaps
+        // with the others (one group per slice instead of all eight warps serialising on every slice).
+        const uint32_t grp = (uint32_t)(warp - 8) >> 1;
+        const uint32_t j = (uint32_t)tid - 256u - grp * 64u;       // 0..63: rows j and j + 64
+        const __nv_bfloat162 off = __floats2bfloat162_rn(136.f, 136.f);
+        uint32_t itR = 0;
+        for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x) {
+            for (uint32_t kq = 0; kq < nkq; kq++, itR++) {
+                const uint32_t rs = itR % a.rawStages, rph = (itR / a.rawStages) & 1;
+                gmBarWait(&rawFull[rs], rph);
+                const uint8_t *rbase = rawBase + (size_t)rs * kGmRawStageBytes;
+                uint4 qv[2][2];
+                uint16_t sv[2][2];
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const uint32_t row = j + 64 * rr;
+#pragma unroll
+                    for (int b = 0; b < 2; b++) {
+                        const uint32_t c8 = grp * 2 + b;
+                        qv[rr][b] = *reinterpret_cast<const uint4 *>(rbase + row * 128 + ((c8 ^ (row & 7)) << 4));
+                        sv[rr][b] = *reinterpret_cast<const uint16_t *>(rbase + kGmRawQsBytes + row * 16 + c8 * 2);
+                    }
+                }
+                const uint32_t itA = itR * 4 + grp;
+                const uint32_t s = itA % a.stages, ph = (itA / a.stages) & 1;
+                gmBarWait(&emptyBar[s], ph ^ 1);
+                uint8_t *aTile = smem + (size_t)s * stageBytes;
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const uint32_t row = j + 64 * rr;
+                    const uint32_t swz = row & 7;
+#pragma unroll
+                    for (int b = 0; b < 2; b++) {
+                        const __nv_bfloat16 sc = __float2bfloat16_rn(__half2float(__ushort_as_half(sv[rr][b])));
+                        const __nv_bfloat162 sc2 = __halves2bfloat162(sc, sc);
+                        const uint32_t w[4] = {qv[rr][b].x, qv[rr][b].y, qv[rr][b].z, qv[rr][b].w};
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int sft = 0; sft < 4; sft++) {
+                                uint32_t t = ((w[c] >> (4 * sft)) & 0x000f000fu) | 0x43004300u;
+                                __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162 *>(&t);
+                                v = __hmul2(__hsub2(v, off), sc2);
+                                o[sft] = *reinterpret_cast<uint32_t *>(&v);
+                            }
+                            const uint32_t chunk = (uint32_t)(b * 4 + c) ^ swz;
+                            if (!(a.debugFlags & 2u)) *reinterpret_cast<uint4 *>(aTile + row * 128 + chunk * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                }
+                if (!(a.debugFlags & 1u)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    gmBarArrive(&fullBar[s]);
+                    gmBarArrive(&rawEmpty[rs]);
+                }
+            }
+        }
+    }
+
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == 2) {
+        tcFenceAfter();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(a.tmemCols) : "memory");
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -285,12 +518,14 @@ static EncodeTiledFn encodeTiled() {
 }
 
 template <int EPI>
-static int launchGemm(const CUtensorMap &map, const GemmArgs &a, int grid, size_t smemBytes, cudaStream_t stream, bool pdl) {
-    auto kernel = gemmQ40TcKernel<EPI>;
-    static size_t configured = 0;
-    if (smemBytes > configured) {
-        DL_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-        configured = smemBytes;
+static int launchGemm(const CUtensorMap &mapB, const CUtensorMap *mapQ, const CUtensorMap *mapS, const GemmArgs &a, int grid,
+                      size_t smemBytes, cudaStream_t stream, bool pdl) {
+    static size_t configured[2] = {0, 0};
+    const int variant = mapQ ? 1 : 0;
+    if (smemBytes > configured[variant]) {
+        if (variant) DL_CUDA_CHECK(cudaFuncSetAttribute(gemmQ40TcTmaKernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        else DL_CUDA_CHECK(cudaFuncSetAttribute(gemmQ40TcKernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        configured[variant] = smemBytes;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -302,48 +537,84 @@ static int launchGemm(const CUtensorMap &map, const GemmArgs &a, int grid, size_
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, map, a));
+    if (variant) DL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemmQ40TcTmaKernel<EPI>, mapB, *mapQ, *mapS, a));
+    else DL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemmQ40TcKernel<EPI>, mapB, a));
     return 0;
 }
 
-// act: bf16 [T][n] row-major (row stride actStride elements). Returns <0 on error.
-int gemmQ40Tc(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T,
-              void *out, uint32_t outStride, int numSms, cudaStream_t stream, bool pdl) {
+static bool encode2d(EncodeTiledFn enc, CUtensorMap *map, CUtensorMapDataType type, const void *base, uint64_t inner, uint64_t outer,
+                     uint64_t strideBytes, uint32_t boxInner, uint32_t boxOuter, CUtensorMapSwizzle swz) {
+    const cuuint64_t dims[2] = {inner, outer};
+    const cuuint64_t strides[1] = {strideBytes};
+    const cuuint32_t box[2] = {boxInner, boxOuter};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, type, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// act: bf16 [T][n] row-major (row stride actStride elements). variant: 0 auto, 1 register-prefetch dequant, 2 TMA-staged raw weights.
+int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T,
+               void *out, uint32_t outStride, int numSms, cudaStream_t stream, bool pdl, int variant) {
     if (T == 0 || T > 256 || n % kGmBlockK || d % 2) return -1;
     EncodeTiledFn enc = encodeTiled();
     if (!enc) return -2;
+    bool tma = variant == 2 || (variant == 0 && n % 256 == 0);
+    if (tma && n % 256) return -6;
     GemmArgs a{};
     a.qs = (const uint32_t *)qs; a.scales = (const __half *)scales; a.d = d; a.n = n; a.T = T;
     a.nTile = (T + 15) / 16 * 16;
     a.out = out; a.outStride = outStride;
+    { const char *dbg = getenv("DL_GEMM_DEBUG"); a.debugFlags = dbg ? (uint32_t)atoi(dbg) : 0u; }
     uint32_t cols = 32;
     while (cols < 2 * a.nTile) cols *= 2;
     a.tmemCols = cols;
     const size_t stageBytes = kGmATileBytes + (size_t)a.nTile * 128;
-    uint32_t stages = (uint32_t)((200 * 1024) / stageBytes);
-    if (stages > (uint32_t)kGmMaxStages) stages = kGmMaxStages;
-    if (stages < 2) return -3;
+    const size_t budget = 227 * 1024 - 1024 - 512;
+    size_t rawBytes = 0;
+    uint32_t stages = 0;
+    if (tma) {
+        // Each dequant group owns every 4th k-slice, so a pipeline stage must always be revisited by the same group
+        // (mbarrier parity waits only disambiguate adjacent phases): the stage count has to be a multiple of 4.
+        const uint32_t tryRaw[3] = {3, 3, 2}, tryStages[3] = {8, 4, 4};
+        for (int i = 0; i < 3 && !stages; i++)
+            if (tryStages[i] * stageBytes + (size_t)tryRaw[i] * kGmRawStageBytes <= budget) { stages = tryStages[i]; a.rawStages = tryRaw[i]; }
+        if (!stages) {
+            if (variant == 2) return -9;
+            tma = false;
+        } else {
+            rawBytes = (size_t)a.rawStages * kGmRawStageBytes;
+        }
+    }
+    if (!tma) {
+        stages = (uint32_t)(budget / stageBytes);
+        if (stages > (uint32_t)kGmMaxStages) stages = kGmMaxStages;
+        if (stages < 2) return -3;
+    }
     a.stages = stages;
-    const size_t smemBytes = stages * stageBytes + 1024 + 512;
+    const size_t smemBytes = stages * stageBytes + rawBytes + 1024 + 512;
 
-    CUtensorMap map;
-    const cuuint64_t dims[2] = {n, T};
-    const cuuint64_t strides[1] = {(cuuint64_t)actStride * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kGmBlockK, a.nTile};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(act), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return -4;
+    CUtensorMap mapB, mapQ, mapS;
+    if (!encode2d(enc, &mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, act, n, T, (uint64_t)actStride * 2, kGmBlockK, a.nTile, CU_TENSOR_MAP_SWIZZLE_128B))
+        return -4;
+    if (tma) {
+        if (!encode2d(enc, &mapQ, CU_TENSOR_MAP_DATA_TYPE_UINT8, qs, n / 2, d, n / 2, 128, kGmBlockM, CU_TENSOR_MAP_SWIZZLE_128B)) return -7;
+        if (!encode2d(enc, &mapS, CU_TENSOR_MAP_DATA_TYPE_UINT8, scales, n / 16, d, n / 16, 16, kGmBlockM, CU_TENSOR_MAP_SWIZZLE_NONE)) return -8;
+    }
     const uint32_t nTilesM = (d + kGmBlockM - 1) / kGmBlockM;
     const int grid = (int)(nTilesM < (uint32_t)numSms ? nTilesM : (uint32_t)numSms);
+    const CUtensorMap *pq = tma ? &mapQ : nullptr, *ps = tma ? &mapS : nullptr;
     switch (epi) {
-        case GEPI_STORE_F32: return launchGemm<GEPI_STORE_F32>(map, a, grid, smemBytes, stream, pdl);
-        case GEPI_RESIDUAL: return launchGemm<GEPI_RESIDUAL>(map, a, grid, smemBytes, stream, pdl);
-        case GEPI_SWIGLU_BF16: return launchGemm<GEPI_SWIGLU_BF16>(map, a, grid, smemBytes, stream, pdl);
-        case GEPI_STORE_BF16: return launchGemm<GEPI_STORE_BF16>(map, a, grid, smemBytes, stream, pdl);
+        case GEPI_STORE_F32: return launchGemm<GEPI_STORE_F32>(mapB, pq, ps, a, grid, smemBytes, stream, pdl);
+        case GEPI_RESIDUAL: return launchGemm<GEPI_RESIDUAL>(mapB, pq, ps, a, grid, smemBytes, stream, pdl);
+        case GEPI_SWIGLU_BF16: return launchGemm<GEPI_SWIGLU_BF16>(mapB, pq, ps, a, grid, smemBytes, stream, pdl);
+        case GEPI_STORE_BF16: return launchGemm<GEPI_STORE_BF16>(mapB, pq, ps, a, grid, smemBytes, stream, pdl);
     }
     return -5;
+}
+
+int gemmQ40Tc(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T,
+              void *out, uint32_t outStride, int numSms, cudaStream_t stream, bool pdl) {
+    return gemmQ40TcV(epi, qs, scales, d, n, act, actStride, T, out, outStride, numSms, stream, pdl, 0);
 }
 
 // ---- rmsnorm -> bf16 (activation operand producer) ------------------------------------------------------------------
@@ -384,8 +655,8 @@ int launchRmsNormBf16(const float *x, uint32_t xStride, const float *w, void *y,
 }  // namespace dl
 
 DL_EXPORT int dl_gemm_q40_tc(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride,
-                             uint32_t T, void *out, uint32_t outStride, int numSms, cudaStream_t stream, int pdl) {
-    return dl::gemmQ40Tc(epi, qs, scales, d, n, act, actStride, T, out, outStride, numSms, stream, pdl != 0);
+                             uint32_t T, void *out, uint32_t outStride, int numSms, cudaStream_t stream, int pdl, int variant) {
+    return dl::gemmQ40TcV(epi, qs, scales, d, n, act, actStride, T, out, outStride, numSms, stream, pdl != 0, variant);
 }
 
 DL_EXPORT int dl_rmsnorm_bf16(const float *x, uint32_t xStride, const float *w, void *y, uint32_t yStride, uint32_t n, float eps,

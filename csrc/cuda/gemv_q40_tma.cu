@@ -242,13 +242,14 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
         const uint4 *sq = reinterpret_cast<const uint4 *>(stage);
         const uint16_t *ss = reinterpret_cast<const uint16_t *>(stage + (size_t)SR * rowQsBytes);
         // steps are dealt round-robin over the 16 warps *across* fills (a stage may hold fewer than 16 steps)
-        const uint32_t stepsPerFullStage = (SR / kRowsPerStep > 0 ? SR / kRowsPerStep : 1) * nseg;
+        const uint32_t stepsPerFullStage = (SR / kRowsPerStep) * nseg;
         const uint32_t firstStep = (warp + kConsumerWarps - (f * stepsPerFullStage) % kConsumerWarps) % kConsumerWarps;
         // every warp waits (even one without steps in this fill): it keeps all warps within one ring revolution, so no
         // warp can arrive twice on the same empty-barrier phase
         mbarWait(&fullBar[st], (f / geo.nStages) & 1);
+        uint32_t g = firstStep / nseg, seg = firstStep - g * nseg;            // one division per fill, then incremental
+        const uint32_t gInc = kConsumerWarps / nseg, segInc = kConsumerWarps - gInc * nseg;
         for (uint32_t s = firstStep; s < nSteps; s += kConsumerWarps) {
-            const uint32_t g = s / nseg, seg = s - g * nseg;
             const uint32_t blk = seg * 32 + lane;
             const uint32_t rl = g * kRowsPerStep;                  // first row of the group inside the stage
             float acc[kRowsPerStep][NB];
@@ -261,33 +262,36 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
                 float dxv[NB], dx8v[NB];
 #pragma unroll
                 for (int t = 0; t < NB; t++) {
-                    A[t] = planeA[(size_t)t * nblk + blk];
-                    B[t] = planeB[(size_t)t * nblk + blk];
-                    dxv[t] = dxs[(size_t)t * nblk + blk];
-                    dx8v[t] = dx8[(size_t)t * nblk + blk];
+                    A[t] = planeA[t * nblk + blk];
+                    B[t] = planeB[t * nblk + blk];
+                    dxv[t] = dxs[t * nblk + blk];
+                    dx8v[t] = dx8[t * nblk + blk];
                 }
+                // Rows past the end of a short last stage read stale ring bytes (always inside the stage buffer because
+                // stageRows % 4 == 0); their sums are simply not stored below, so no branch is needed here.
+                const uint4 *qp = sq + rl * nblk + blk;
+                const uint16_t *sp = ss + rl * nblk + blk;
 #pragma unroll
                 for (int r = 0; r < kRowsPerStep; r++) {
-                    if (rl + r < rows) {   // warp-uniform
-                        const uint4 q = sq[(size_t)(rl + r) * nblk + blk];
-                        const float dw = __half2float(__ushort_as_half(ss[(size_t)(rl + r) * nblk + blk]));
-                        const uint32_t m = 0x0f0f0f0fu;
-                        const uint32_t l0 = q.x & m, h0 = (q.x >> 4) & m;
-                        const uint32_t l1 = q.y & m, h1 = (q.y >> 4) & m;
-                        const uint32_t l2 = q.z & m, h2 = (q.z >> 4) & m;
-                        const uint32_t l3 = q.w & m, h3 = (q.w >> 4) & m;
+                    const uint4 q = qp[r * nblk];
+                    const float dw = __half2float(__ushort_as_half(sp[r * nblk]));
+                    // low nibbles: q & 0x0f0f0f0f; high nibbles are used in place (q & 0xf0f0f0f0 = 16 * nibble), the factor
+                    // 16 is removed with one shift after the dot product (exact: the partial sum is a multiple of 16)
+                    const uint32_t ml = 0x0f0f0f0fu, mh = 0xf0f0f0f0u;
+                    const uint32_t l0 = q.x & ml, h0 = q.x & mh, l1 = q.y & ml, h1 = q.y & mh;
+                    const uint32_t l2 = q.z & ml, h2 = q.z & mh, l3 = q.w & ml, h3 = q.w & mh;
 #pragma unroll
-                        for (int t = 0; t < NB; t++) {
-                            int dot = dp4a(l0, A[t].x, 0);
-                            dot = dp4a(h0, B[t].x, dot);
-                            dot = dp4a(l1, A[t].y, dot);
-                            dot = dp4a(h1, B[t].y, dot);
-                            dot = dp4a(l2, A[t].z, dot);
-                            dot = dp4a(h2, B[t].z, dot);
-                            dot = dp4a(l3, A[t].w, dot);
-                            dot = dp4a(h3, B[t].w, dot);
-                            acc[r][t] = dw * (dxv[t] * (float)dot - dx8v[t]);
-                        }
+                    for (int t = 0; t < NB; t++) {
+                        int lo = dp4a(l0, A[t].x, 0);
+                        int hi = dp4a(h0, B[t].x, 0);
+                        lo = dp4a(l1, A[t].y, lo);
+                        hi = dp4a(h1, B[t].y, hi);
+                        lo = dp4a(l2, A[t].z, lo);
+                        hi = dp4a(h2, B[t].z, hi);
+                        lo = dp4a(l3, A[t].w, lo);
+                        hi = dp4a(h3, B[t].w, hi);
+                        const int dot = lo + (hi >> 4);
+                        acc[r][t] = dw * (dxv[t] * (float)dot - dx8v[t]);
                     }
                 }
             }
@@ -296,9 +300,12 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
                 const float v = reduce4(acc[0][t], acc[1][t], acc[2][t], acc[3][t], lane);
                 if ((lane & 7) == 0) {
                     const uint32_t r = lane >> 3;
-                    if (rl + r < rows) partial[((size_t)(r0 + rl + r) * nseg + seg) * NB + t] = v;
+                    if (rl + r < rows) partial[((r0 + rl + r) * nseg + seg) * NB + t] = v;
                 }
             }
+            g += gInc;
+            seg += segInc;
+            if (seg >= nseg) { seg -= nseg; g++; }
         }
         __syncwarp();
         if (lane == 0) mbarArrive(&emptyBar[st]);
@@ -514,7 +521,7 @@ int gemvQ40Tma(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t st
     uint32_t sr = (64 + nseg - 1) / nseg;
     sr = (sr + 3) / 4 * 4;
     while (sr > 4 && sr * rowBytes > 36 * 1024) sr -= 4;
-    if (sr * rowBytes > 36 * 1024) sr = 2;
+    if (sr * rowBytes > 48 * 1024) return 1;   // rows too wide for a 4-row stage: per-thread-load kernel handles it
     if (sr > 64) sr = 64;
     geo.stageRows = sr;
     geo.stageBytes = (sr * rowBytes + 127) / 128 * 128;

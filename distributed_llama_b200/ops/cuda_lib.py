@@ -54,7 +54,7 @@ def lib() -> C.CDLL:
     L.dl_dequant_device_q40.restype = i32
     L.dl_gemv_q40.argtypes = [i32, i32, i32, vp, vp, u32, u32, vp, u32, vp, f32, vp, u32, i32, vp, i32, i32]
     L.dl_gemv_q40.restype = i32
-    L.dl_gemm_q40_tc.argtypes = [i32, vp, vp, u32, u32, vp, u32, u32, vp, u32, i32, vp, i32]
+    L.dl_gemm_q40_tc.argtypes = [i32, vp, vp, u32, u32, vp, u32, u32, vp, u32, i32, vp, i32, i32]
     L.dl_gemm_q40_tc.restype = i32
     L.dl_rmsnorm_bf16.argtypes = [vp, u32, vp, vp, u32, u32, f32, u32, vp]
     L.dl_rmsnorm_bf16.restype = i32

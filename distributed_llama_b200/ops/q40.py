@@ -55,13 +55,15 @@ def gemv_q40(w: DeviceQ40, x: torch.Tensor, *, pro: int, epi: int, out: torch.Te
     return out
 
 
-def gemm_q40_tc(w: DeviceQ40, act: torch.Tensor, *, epi: int, out: torch.Tensor, num_sms: int = 0, pdl: bool = False) -> torch.Tensor:
+def gemm_q40_tc(w: DeviceQ40, act: torch.Tensor, *, epi: int, out: torch.Tensor, num_sms: int = 0, pdl: bool = False,
+                variant: str = "auto") -> torch.Tensor:
     """tcgen05 prefill GEMM. act: bf16 [T, n] (T <= 256); out: [T, d] f32 (STORE/RESIDUAL), bf16 [T, d/2] (SWIGLU) or bf16 [T, d]."""
     assert act.dtype == torch.bfloat16 and act.is_cuda and act.stride(1) == 1
     if num_sms == 0:
         num_sms = torch.cuda.get_device_properties(act.device).multi_processor_count
     cl.check(cl.lib().dl_gemm_q40_tc(epi, w.qs.data_ptr(), w.scales.data_ptr(), w.d, w.n, act.data_ptr(), act.stride(0), act.shape[0],
-                                     out.data_ptr(), out.stride(0), num_sms, cl.stream_ptr(), 1 if pdl else 0), "gemm_q40_tc")
+                                     out.data_ptr(), out.stride(0), num_sms, cl.stream_ptr(), 1 if pdl else 0,
+                                     {"auto": 0, "ldg": 1, "tma": 2}[variant]), "gemm_q40_tc")
     return out
 
 

@@ -23,7 +23,7 @@ def _p(t: Optional[torch.Tensor]):
 
 class Engine:
     def __init__(self, weights: DeviceWeights, max_batch: int = 8, n_splits: int = 0, use_pdl: bool = True,
-                 seq_len: Optional[int] = None, comm=None, max_prefill: int = 256):
+                 seq_len: Optional[int] = None, comm=None, max_prefill: int = 192):
         self.w = w = weights
         h = w.header
         dev = w.embedding.device

@@ -8,16 +8,19 @@ pytestmark = pytest.mark.gpu
 from test_gpu_kernels import _rand_q40, _device_q40   # noqa: E402
 
 
+@pytest.mark.parametrize("variant", ["ldg", "tma"])
 @pytest.mark.parametrize("d,n,T", [(256, 256, 16), (128, 64, 1), (384, 512, 17), (6144, 4096, 64), (4096, 14336, 64),
-                                   (1024, 1792, 200), (2048, 4096, 256), (1000, 2176, 33)])
-def test_gemm_store_f32(d, n, T):
+                                   (1024, 1792, 200), (2048, 4096, 256), (1000, 2176, 33), (28672, 4096, 100), (4096, 4096, 192)])
+def test_gemm_store_f32(d, n, T, variant):
+    if variant == "tma" and (n % 256 or T > 208):
+        pytest.skip("TMA-staged variant needs n % 256 == 0 and room for 4 pipeline stages")
     from distributed_llama_b200 import ops
     raw, wq = _rand_q40(d, n, seed=5)
     w = _device_q40(raw, d, n)
     torch.manual_seed(2)
     act = torch.randn(T, n, device="cuda").bfloat16()
     out = torch.full((T, d), float("nan"), device="cuda")
-    ops.gemm_q40_tc(w, act, epi=ops.GEPI_STORE_F32, out=out)
+    ops.gemm_q40_tc(w, act, epi=ops.GEPI_STORE_F32, out=out, variant=variant)
     torch.cuda.synchronize()
     ref = act.float() @ torch.from_numpy(wq).cuda().T
     err = (out - ref).abs().max().item()
