@@ -137,6 +137,8 @@ def run_ours(args):
     t0 = time.time()
     sess = InferenceSession(model_path, tok_path, max_seq_len=args.max_seq_len, temperature=0.0, comm=comm)
     eng = sess.engine
+    if args.decode_path == "mega":
+        eng.enable_mega()
     log(f"[bench] rank {rank}: weights on device in {time.time() - t0:.1f}s ({sess.weights.bytes_uploaded / 1e9:.2f} GB uploaded)")
 
     steps, warmup = args.steps, max(args.warmup, 3)
@@ -356,6 +358,7 @@ def main():
     ap.add_argument("--prompt-len", type=int, default=64)
     ap.add_argument("--max-seq-len", type=int, default=2048)
     ap.add_argument("--ref-timeout", type=int, default=1500)
+    ap.add_argument("--decode-path", default="multi", choices=["multi", "mega"], help="multi-kernel PDL chain or persistent megakernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -83,6 +83,9 @@ struct Engine {
     int lastError = 0;
     uint64_t *trace = nullptr;   // device buffer [maxLaunches][4] of globaltimer stamps (optional)
     uint32_t traceCap = 0;
+    MegaLayer *megaLayers = nullptr;   // device copy of the per-layer pointer table for the persistent decode kernel
+    unsigned int *megaCounter = nullptr;
+    bool useMega = false;
     bool fusedAttn = true, fusedArgmax = true, useTma = true;   // debugging switches (DL_NO_FUSED_ATTN / DL_NO_FUSED_ARGMAX / DL_NO_TMA)
 };
 
@@ -110,12 +113,35 @@ static int gemvSel(const Engine &e, int pro, int epi, int nb, const GemvArgs &a,
     return e.useTma ? gemvQ40Auto(pro, epi, nb, a, numSms, stream, pdl) : gemvQ40(pro, epi, nb, a, numSms, stream, pdl);
 }
 
+// One token through the persistent kernel (dense models, nb == 1). Returns 1 when the shape is not supported.
+static int engineDecodeMega(Engine &e, bool greedyAdvance, cudaStream_t stream) {
+    const EngineConfig &c = e.cfg;
+    if (!e.megaLayers || c.nExperts > 0) return 1;
+    MegaArgs m{};
+    m.layers = e.megaLayers; m.nLayers = c.nLayers; m.dim = c.dim; m.nHeads = c.nHeads; m.nKvHeads = c.nKvHeads; m.headDim = c.headDim;
+    m.ffDim = c.ffDim; m.vocab = c.vocab; m.vocabFull = e.g.vocabFull; m.seqLen = c.seqLen; m.nSplits = c.nSplits; m.eps = c.eps;
+    m.embedding = e.g.embedding; m.finalNorm = e.g.finalNorm; m.rope = e.g.rope;
+    m.wclsQs = (const uint8_t *)e.g.wclsQs; m.wclsSc = (const uint8_t *)e.g.wclsSc;
+    m.tokens = e.g.tokens; m.pos = e.g.pos; m.history = e.g.history;
+    m.x = e.g.x; m.qkv = e.g.qkv; m.z = e.g.z; m.h = e.g.h; m.logits = e.g.logits;
+    m.attnPartial = e.g.attnPartial; m.attnCounters = e.g.attnCounters;
+    m.argVal = e.g.argVal; m.argIdx = e.g.argIdx; m.argCounter = e.g.argCounter; m.gridCounter = e.megaCounter;
+    m.rowOffsetGlobal = c.rank * c.vocab; m.greedyAdvance = greedyAdvance ? 1u : 0u;
+    m.trace = e.trace;
+    if (e.comm.nRanks > 1) fillAr(e, m.ar, 0);
+    return launchMegaDecode(m, (int)c.numSms, stream);
+}
+
 // logitsMode: 0 = none (prefill chunk), 1 = logits of the last token in the batch into logits[0], 2 = all tokens
 static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, cudaStream_t stream) {
     const EngineConfig &c = e.cfg;
     const bool pdl = c.usePdl != 0;
     const uint32_t qDim = c.nHeads * c.headDim, kvDim = c.nKvHeads * c.headDim, qkvDim = qDim + 2 * kvDim;
     if (nb < 1 || (uint32_t)nb > c.maxBatch || (nb & (nb - 1))) return -10;
+    if (nb == 1 && logitsMode == 1 && e.useMega) {
+        const int r = engineDecodeMega(e, greedyAdvance, stream);
+        if (r != 1) return r;
+    }
     uint32_t slot = 0;
     auto nextTrace = [&]() -> uint64_t * { uint64_t *t = (e.trace && slot < e.traceCap) ? e.trace + (size_t)slot * 4 : nullptr; slot++; return t; };
 
@@ -288,6 +314,8 @@ DL_EXPORT void dl_engine_destroy(void *h) {
     if (!e) return;
     if (e->decodeGraph) cudaGraphExecDestroy(e->decodeGraph);
     if (e->captureStream) cudaStreamDestroy(e->captureStream);
+    if (e->megaLayers) cudaFree(e->megaLayers);
+    if (e->megaCounter) cudaFree(e->megaCounter);
     delete e;
 }
 
@@ -300,6 +328,28 @@ DL_EXPORT int dl_engine_set_layer(void *h, uint32_t layer, const dl::LayerPtrs *
 
 DL_EXPORT int dl_engine_set_globals(void *h, const dl::GlobalPtrs *p) {
     ((Engine *)h)->g = *p;
+    return 0;
+}
+
+// Uploads the per-layer pointer table and switches single-token forwards to the persistent kernel.
+DL_EXPORT int dl_engine_enable_mega(void *h, int enable) {
+    Engine *e = (Engine *)h;
+    if (enable && !e->megaLayers) {
+        std::vector<dl::MegaLayer> tab(e->layers.size());
+        for (size_t l = 0; l < tab.size(); l++) {
+            const dl::LayerPtrs &L = e->layers[l];
+            dl::MegaLayer &m = tab[l];
+            m.qkvQs = (const uint8_t *)L.qkvQs; m.qkvSc = (const uint8_t *)L.qkvSc; m.woQs = (const uint8_t *)L.woQs; m.woSc = (const uint8_t *)L.woSc;
+            m.w13Qs = (const uint8_t *)L.w13Qs; m.w13Sc = (const uint8_t *)L.w13Sc; m.w2Qs = (const uint8_t *)L.w2Qs; m.w2Sc = (const uint8_t *)L.w2Sc;
+            m.norm0 = L.norm0; m.norm1 = L.norm1; m.qNorm = L.qNorm; m.kNorm = L.kNorm;
+            m.kCache = (__nv_bfloat16 *)L.kCache; m.vCache = (__nv_bfloat16 *)L.vCache;
+        }
+        DL_CUDA_CHECK(cudaMalloc(&e->megaLayers, tab.size() * sizeof(dl::MegaLayer)));
+        DL_CUDA_CHECK(cudaMemcpy(e->megaLayers, tab.data(), tab.size() * sizeof(dl::MegaLayer), cudaMemcpyHostToDevice));
+        DL_CUDA_CHECK(cudaMalloc(&e->megaCounter, 256));
+        DL_CUDA_CHECK(cudaMemset(e->megaCounter, 0, 256));
+    }
+    e->useMega = enable != 0;
     return 0;
 }
 

@@ -116,6 +116,36 @@ int launchEmbedding(const float *table, const int *tokens, float *x, uint32_t di
 int launchArgmaxAdvance(const float *logits, uint32_t vocab, int *tokenOut, int *pos, int *history, uint32_t historyCap,
                         cudaStream_t stream, bool pdl);
 
+// Persistent decode kernel (mega_decode.cu)
+struct MegaLayer {
+    const uint8_t *qkvQs, *qkvSc, *woQs, *woSc, *w13Qs, *w13Sc, *w2Qs, *w2Sc;
+    const float *norm0, *norm1, *qNorm, *kNorm;
+    __nv_bfloat16 *kCache, *vCache;
+};
+
+struct MegaArgs {
+    const MegaLayer *layers;     // [nLayers] in global memory
+    uint32_t nLayers, dim, nHeads, nKvHeads, headDim, ffDim, vocab, vocabFull, seqLen, nSplits;
+    float eps;
+    const float *embedding, *finalNorm, *rope;
+    const uint8_t *wclsQs, *wclsSc;
+    int *tokens, *pos, *history;
+    float *x, *qkv, *z, *h, *logits;
+    float *attnPartial;
+    unsigned int *attnCounters;
+    float *argVal;
+    int *argIdx;
+    unsigned int *argCounter;
+    unsigned int *gridCounter;   // zeroed by a memset node before every launch
+    uint32_t stageBytes, nStages, planeBlocks, partialFloats;   // shared-memory geometry (host computed)
+    uint32_t rowOffsetGlobal;
+    uint32_t greedyAdvance;      // 1: publish the arg-max token and advance the position on the device
+    uint64_t *trace;
+    ArArgs ar;
+};
+
+int launchMegaDecode(MegaArgs m, int numSms, cudaStream_t stream);
+
 // tcgen05 prefill GEMM (gemm_q40_tc.cu)
 enum { GEPI_STORE_F32_ = 0, GEPI_RESIDUAL_ = 1, GEPI_SWIGLU_BF16_ = 2, GEPI_STORE_BF16_ = 3 };
 int gemmQ40Tc(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T,

@@ -66,6 +66,8 @@ def lib() -> C.CDLL:
     L.dl_engine_set_layer.restype = i32
     L.dl_engine_set_globals.argtypes = [vp, C.POINTER(GlobalPtrs)]
     L.dl_engine_set_globals.restype = i32
+    L.dl_engine_enable_mega.argtypes = [vp, i32]
+    L.dl_engine_enable_mega.restype = i32
     L.dl_engine_set_comm.argtypes = [vp, C.POINTER(CommPtrs)]
     L.dl_engine_set_comm.restype = i32
     for name, args in (("dl_comm_alloc", [C.c_size_t, C.POINTER(vp)]), ("dl_comm_free", [vp]), ("dl_comm_ipc_handle", [vp, vp]),

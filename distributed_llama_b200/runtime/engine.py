@@ -106,6 +106,7 @@ class Engine:
             cp = comm.comm_ptrs(max_batch * h.dim)
             cl.check(self._lib.dl_engine_set_comm(self._h, C.byref(cp)), "engine_set_comm")
         self.use_tc_prefill = True
+        self.mega = False
         self.tc_min_tokens = 9          # shorter chunks stay on the GEMV path
         self._graph_ready = False
         self._stage_tok = torch.zeros(max_batch, dtype=torch.int32).pin_memory()
@@ -118,6 +119,12 @@ class Engine:
                 self._h = None
         except Exception:
             pass
+
+    def enable_mega(self, enable: bool = True):
+        """Single-token forwards through the persistent per-token kernel (dense models). Re-captures the decode graph."""
+        cl.check(self._lib.dl_engine_enable_mega(self._h, 1 if enable else 0), "engine_enable_mega")
+        self.mega = enable
+        self._graph_ready = False
 
     # -- tracing --
     def enable_trace(self, cap_launches: int = 1024):

@@ -75,3 +75,27 @@ def test_tensor_core_prefill_matches_oracle(tmp_models, name):
     eng_b.use_tc_prefill = False
     lg_b = eng_b.prefill(toks, 0)
     assert (lg - lg_b).abs().max().item() < 0.12
+
+
+@pytest.mark.parametrize("name", ["tiny-llama31", "tiny-qwen3"])
+def test_persistent_decode_kernel(tmp_models, name):
+    """The one-launch-per-token megakernel must reproduce the multi-kernel path (logits close, greedy tokens equal)."""
+    mf, eng, oracle = _setup(tmp_models, name)
+    prompt = [3, 17, 250, 9, 44, 101, 7]
+    eng.prefill(prompt[:-1], 0, want_logits=False)
+    ref_toks = eng.decode_greedy(prompt[-1], len(prompt) - 1, 40)
+    eng_m = _setup(tmp_models, name)[1]
+    eng_m.enable_mega()
+    eng_m.prefill(prompt[:-1], 0, want_logits=False)
+    lg_m = eng_m.step(prompt[-1], len(prompt) - 1).clone()
+    eng_c = _setup(tmp_models, name)[1]
+    eng_c.prefill(prompt[:-1], 0, want_logits=False)
+    lg_c = eng_c.step(prompt[-1], len(prompt) - 1).clone()
+    assert (lg_m - lg_c).abs().max().item() < 2e-3
+    for use_graph in (False, True):
+        e = _setup(tmp_models, name)[1]
+        e.enable_mega()
+        e.prefill(prompt[:-1], 0, want_logits=False)
+        toks = e.decode_greedy(prompt[-1], len(prompt) - 1, 40, use_graph=use_graph)
+        agree = sum(a == b for a, b in zip(toks, ref_toks))
+        assert agree >= 36, (toks, ref_toks)

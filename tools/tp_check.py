@@ -27,7 +27,10 @@ def main():
         write_synthetic_model(path, get_config(name), seed=11)
     dist.barrier()
     mf = ModelFile(path)
+    mega = os.environ.get("DL_MEGA") == "1"
     eng = Engine(load_device_weights(mf, comm.rank, comm.world_size, moe_mode=moe_mode), comm=comm)
+    if mega:
+        eng.enable_mega()
     prompt = [3, 17, 250, 9, 44, 101, 7, 300, 12, 5, 77]
     # logits through the step API (all-gathered across ranks)
     lg = []
@@ -36,9 +39,13 @@ def main():
     lg = torch.stack(lg)
     # greedy decode on the device (cross-rank arg-max inside the logits kernel), graph replay
     eng2 = Engine(load_device_weights(mf, comm.rank, comm.world_size, moe_mode=moe_mode), comm=comm)
+    if mega:
+        eng2.enable_mega()
     eng2.prefill(prompt[:-1], 0, want_logits=False)
     toks_graph = eng2.decode_greedy(prompt[-1], len(prompt) - 1, 32, use_graph=True)
     eng3 = Engine(load_device_weights(mf, comm.rank, comm.world_size, moe_mode=moe_mode), comm=comm)
+    if mega:
+        eng3.enable_mega()
     eng3.prefill(prompt[:-1], 0, want_logits=False)
     toks_eager = eng3.decode_greedy(prompt[-1], len(prompt) - 1, 32, use_graph=False)
     # every rank must have produced the same tokens
@@ -62,6 +69,7 @@ def main():
         print(f"moe_mode={eng.w.moe_mode} tp={comm.world_size} max|tp - tp1|={e1:.4g} max|tp - oracle|={e2:.4g} greedy agree {n_agree}/32 "
               f"graph==eager {toks_graph == toks_eager} ranks agree {same_across_ranks}")
         ok = e1 < 0.05 and e2 < 0.08 and toks_graph == toks_eager and same_across_ranks and n_agree >= 8
+        print("mega" if mega else "multi-kernel", "decode path")
         print("TP_CHECK", "PASS" if ok else "FAIL")
     dist.barrier()
     dist.destroy_process_group()
