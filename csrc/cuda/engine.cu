@@ -71,6 +71,8 @@ struct CommPtrs {   // mirrored by ctypes
     uint32_t nRanks, rank, maxCtas, slotStride;
     void *arena[kMaxRanks];          // every rank's symmetric arena mapped into this process
     uint64_t slotsOff, flagsOff, candValOff, candIdxOff, candFlagOff, gatherOff;
+    uint64_t prefillSlotsOff;        // LL slots for the prefill GEMM all-reduce: [2][nRanks][maxPrefill * dim]
+    uint32_t prefillSlotStride;
 };
 
 struct Engine {
@@ -258,7 +260,14 @@ static int enginePrefill(Engine &e, uint32_t T, int wantLogits, cudaStream_t str
     const bool pdl = false;   // plain stream order between the heterogeneous kernels of this path
     const uint32_t qDim = c.nHeads * c.headDim, kvDim = c.nKvHeads * c.headDim, qkvDim = qDim + 2 * kvDim;
     if (T < 1 || T > g.maxPrefill || T > 256) return -11;
-    if (e.comm.nRanks > 1) return -12;   // tensor-parallel prefill runs on the GEMV path (fused all-reduce)
+    const bool tp = e.comm.nRanks > 1;
+    ArArgs arP{};
+    if (tp) {
+        if (e.comm.prefillSlotStride < T * c.dim) return -12;
+        fillAr(e, arP, 0);
+        arP.slotStride = e.comm.prefillSlotStride;
+        for (uint32_t r = 0; r < e.comm.nRanks; r++) arP.slots[r] = (uint64_t *)((uint8_t *)e.comm.arena[r] + e.comm.prefillSlotsOff);
+    }
     DL_TRY(launchEmbedding(g.embedding, g.pTokens, g.px, c.dim, c.dim, g.vocabFull, (int)T, stream));
     for (uint32_t l = 0; l < c.nLayers; l++) {
         const LayerPtrs &L = e.layers[l];
@@ -274,10 +283,12 @@ static int enginePrefill(Engine &e, uint32_t T, int wantLogits, cudaStream_t str
         t.nHeads = c.nHeads; t.nKvHeads = c.nKvHeads; t.headDim = c.headDim; t.seqLen = c.seqLen; t.nSplits = 1;
         t.partial = g.pAttnPartial; t.counters = g.pAttnCounters; t.out = nullptr; t.outStride = qDim; t.outBf16 = (__nv_bfloat16 *)g.pzb;
         DL_TRY(launchAttnDecode(t, (int)T, stream, pdl));
-        DL_TRY(gemmQ40Tc(GEPI_RESIDUAL_, L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, pdl));
+        if (tp) { arP.parity = 0; DL_TRY(gemmQ40TcAr(L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, arP)); }
+        else DL_TRY(gemmQ40Tc(GEPI_RESIDUAL_, L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, pdl));
         DL_TRY(launchRmsNormBf16(g.px, c.dim, L.norm1, g.pxn, c.dim, c.dim, c.eps, T, stream));
         DL_TRY(gemmQ40Tc(GEPI_SWIGLU_BF16_, L.w13Qs, L.w13Sc, 2 * c.ffDim, c.dim, g.pxn, c.dim, T, g.phb, c.ffDim, c.numSms, stream, pdl));
-        DL_TRY(gemmQ40Tc(GEPI_RESIDUAL_, L.w2Qs, L.w2Sc, c.dim, c.ffDim, g.phb, c.ffDim, T, g.px, c.dim, c.numSms, stream, pdl));
+        if (tp) { arP.parity = 1; DL_TRY(gemmQ40TcAr(L.w2Qs, L.w2Sc, c.dim, c.ffDim, g.phb, c.ffDim, T, g.px, c.dim, c.numSms, stream, arP)); }
+        else DL_TRY(gemmQ40Tc(GEPI_RESIDUAL_, L.w2Qs, L.w2Sc, c.dim, c.ffDim, g.phb, c.ffDim, T, g.px, c.dim, c.numSms, stream, pdl));
     }
     if (wantLogits) {
         GemvArgs a{};

@@ -28,7 +28,7 @@ constexpr int kGmDeqWarps = 8;
 constexpr int kGmMaxStages = 8;
 constexpr int kGmATileBytes = kGmBlockM * kGmBlockK * 2;   // 16 KB
 
-enum { GEPI_STORE_F32 = 0, GEPI_RESIDUAL = 1, GEPI_SWIGLU_BF16 = 2, GEPI_STORE_BF16 = 3 };
+enum { GEPI_STORE_F32 = 0, GEPI_RESIDUAL = 1, GEPI_SWIGLU_BF16 = 2, GEPI_STORE_BF16 = 3, GEPI_RESIDUAL_AR = 4 };
 
 struct GemmArgs {
     const uint32_t *qs;
@@ -38,6 +38,7 @@ struct GemmArgs {
     void *out;
     uint32_t outStride;   // elements between tokens
     uint32_t stages, tmemCols;
+    ArArgs ar;             // GEPI_RESIDUAL_AR: tensor-parallel all-reduce fused into the epilogue (LL words over peer memory)
     uint32_t rawStages;    // TMA-staged variant: depth of the raw q40 ring (2 or 3)
     uint32_t debugFlags;   // bit0: skip the proxy fence, bit1: skip the A-tile stores (timing experiments only)
 };
@@ -401,6 +402,64 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             tcFenceAfter();
             const uint32_t f = tile * kGmBlockM + q * 32 + lane;
             const bool fOk = f < a.d;
+            if (EPI == GEPI_RESIDUAL_AR) {
+                // ---- GEMM + all-reduce in one kernel: the accumulator tile goes from TMEM straight into LL words of
+                // every rank's slot[myRank] (NVLink peer stores, 256 B per warp store); after the TMEM buffer is released
+                // the same threads poll the slots of all source ranks for their (token, feature) cells, sum them in rank
+                // order, add the residual and clear the words.
+                const ArArgs &ar = a.ar;
+                const size_t slotBase = (size_t)(ar.parity * ar.nRanks + ar.rank) * ar.slotStride;
+                for (uint32_t c0 = 0; c0 < nTile; c0 += 16) {
+                    uint32_t r[16];
+                    tmemLoad16(tmemBase + ((q * 32u) << 16) + acc * nTile + c0, r);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const uint32_t tok = c0 + j;
+                        if (tok < a.T && fOk) {
+                            const size_t off = slotBase + (size_t)tok * ar.dim + f;
+#pragma unroll 1
+                            for (uint32_t p = 0; p < ar.nRanks; p++) stLL(ar.slots[(ar.rank + p) % ar.nRanks] + off, r[j], 1u);
+                        }
+                    }
+                }
+                tcFenceBefore();
+                __syncwarp();
+                if (lane == 0) gmBarArrive(&tmemEmpty[acc]);
+                if (fOk) {
+                    uint64_t *mine = ar.slots[ar.rank];
+                    for (uint32_t tok0 = 0; tok0 < a.T; tok0 += 16) {
+                        float sum[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) sum[j] = 0.f;
+                        for (uint32_t sr = 0; sr < ar.nRanks; sr++) {
+                            uint64_t *base = mine + (size_t)(ar.parity * ar.nRanks + sr) * ar.slotStride + f;
+                            uint2 v[16];
+                            bool all;
+                            do {   // 16 independent loads in flight per poll round
+                                all = true;
+#pragma unroll
+                                for (int j = 0; j < 16; j++) {
+                                    v[j] = (tok0 + j < a.T) ? ldLL(base + (size_t)(tok0 + j) * ar.dim) : make_uint2(0u, 1u);
+                                    all = all && v[j].y != 0u;
+                                }
+                            } while (!all);
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                sum[j] += __uint_as_float(v[j].x);
+                                if (tok0 + j < a.T) stLL(base + (size_t)(tok0 + j) * ar.dim, 0u, 0u);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            if (tok0 + j < a.T) {
+                                float *o = reinterpret_cast<float *>(a.out) + (size_t)(tok0 + j) * a.outStride + f;
+                                *o = __ldcg(o) + sum[j];
+                            }
+                        }
+                    }
+                }
+                continue;
+            }
             for (uint32_t c0 = 0; c0 < nTile; c0 += 16) {
                 uint32_t r[16];
                 float resid[16];
@@ -524,7 +583,7 @@ static int launchGemm(const CUtensorMap &mapB, const CUtensorMap *mapQ, const CU
     const int variant = mapQ ? 1 : 0;
     if (smemBytes > configured[variant]) {
         if (variant) DL_CUDA_CHECK(cudaFuncSetAttribute(gemmQ40TcTmaKernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-        else DL_CUDA_CHECK(cudaFuncSetAttribute(gemmQ40TcKernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        else DL_CUDA_CHECK(cudaFuncSetAttribute(gemmQ40TcKernel<(EPI == GEPI_RESIDUAL_AR ? GEPI_RESIDUAL : EPI)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
         configured[variant] = smemBytes;
     }
     cudaLaunchConfig_t cfg{};
@@ -538,7 +597,7 @@ static int launchGemm(const CUtensorMap &mapB, const CUtensorMap *mapQ, const CU
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (variant) DL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemmQ40TcTmaKernel<EPI>, mapB, *mapQ, *mapS, a));
-    else DL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemmQ40TcKernel<EPI>, mapB, a));
+    else DL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemmQ40TcKernel<(EPI == GEPI_RESIDUAL_AR ? GEPI_RESIDUAL : EPI)>, mapB, a));
     return 0;
 }
 
@@ -554,7 +613,7 @@ static bool encode2d(EncodeTiledFn enc, CUtensorMap *map, CUtensorMapDataType ty
 
 // act: bf16 [T][n] row-major (row stride actStride elements). variant: 0 auto, 1 register-prefetch dequant, 2 TMA-staged raw weights.
 int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T,
-               void *out, uint32_t outStride, int numSms, cudaStream_t stream, bool pdl, int variant) {
+               void *out, uint32_t outStride, int numSms, cudaStream_t stream, bool pdl, int variant, const ArArgs *ar) {
     if (T == 0 || T > 256 || n % kGmBlockK || d % 2) return -1;
     EncodeTiledFn enc = encodeTiled();
     if (!enc) return -2;
@@ -564,6 +623,7 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
     a.qs = (const uint32_t *)qs; a.scales = (const __half *)scales; a.d = d; a.n = n; a.T = T;
     a.nTile = (T + 15) / 16 * 16;
     a.out = out; a.outStride = outStride;
+    if (ar) a.ar = *ar;
     { const char *dbg = getenv("DL_GEMM_DEBUG"); a.debugFlags = dbg ? (uint32_t)atoi(dbg) : 0u; }
     uint32_t cols = 32;
     while (cols < 2 * a.nTile) cols *= 2;
@@ -608,13 +668,21 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
         case GEPI_RESIDUAL: return launchGemm<GEPI_RESIDUAL>(mapB, pq, ps, a, grid, smemBytes, stream, pdl);
         case GEPI_SWIGLU_BF16: return launchGemm<GEPI_SWIGLU_BF16>(mapB, pq, ps, a, grid, smemBytes, stream, pdl);
         case GEPI_STORE_BF16: return launchGemm<GEPI_STORE_BF16>(mapB, pq, ps, a, grid, smemBytes, stream, pdl);
+        case GEPI_RESIDUAL_AR:
+            if (!tma || !ar) return -10;
+            return launchGemm<GEPI_RESIDUAL_AR>(mapB, pq, ps, a, grid, smemBytes, stream, pdl);
     }
     return -5;
 }
 
 int gemmQ40Tc(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T,
               void *out, uint32_t outStride, int numSms, cudaStream_t stream, bool pdl) {
-    return gemmQ40TcV(epi, qs, scales, d, n, act, actStride, T, out, outStride, numSms, stream, pdl, 0);
+    return gemmQ40TcV(epi, qs, scales, d, n, act, actStride, T, out, outStride, numSms, stream, pdl, 0, nullptr);
+}
+
+int gemmQ40TcAr(const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T, void *out,
+                uint32_t outStride, int numSms, cudaStream_t stream, const ArArgs &ar) {
+    return gemmQ40TcV(GEPI_RESIDUAL_AR, qs, scales, d, n, act, actStride, T, out, outStride, numSms, stream, false, 2, &ar);
 }
 
 // ---- rmsnorm -> bf16 (activation operand producer) ------------------------------------------------------------------
@@ -656,7 +724,7 @@ int launchRmsNormBf16(const float *x, uint32_t xStride, const float *w, void *y,
 
 DL_EXPORT int dl_gemm_q40_tc(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride,
                              uint32_t T, void *out, uint32_t outStride, int numSms, cudaStream_t stream, int pdl, int variant) {
-    return dl::gemmQ40TcV(epi, qs, scales, d, n, act, actStride, T, out, outStride, numSms, stream, pdl != 0, variant);
+    return dl::gemmQ40TcV(epi, qs, scales, d, n, act, actStride, T, out, outStride, numSms, stream, pdl != 0, variant, nullptr);
 }
 
 DL_EXPORT int dl_rmsnorm_bf16(const float *x, uint32_t xStride, const float *w, void *y, uint32_t yStride, uint32_t n, float eps,

@@ -150,6 +150,8 @@ int launchMegaDecode(MegaArgs m, int numSms, cudaStream_t stream);
 enum { GEPI_STORE_F32_ = 0, GEPI_RESIDUAL_ = 1, GEPI_SWIGLU_BF16_ = 2, GEPI_STORE_BF16_ = 3 };
 int gemmQ40Tc(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T,
               void *out, uint32_t outStride, int numSms, cudaStream_t stream, bool pdl);
+int gemmQ40TcAr(const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T, void *out,
+                uint32_t outStride, int numSms, cudaStream_t stream, const ArArgs &ar);   // GEMM + fused all-reduce + residual
 int launchRmsNormBf16(const float *x, uint32_t xStride, const float *w, void *y, uint32_t yStride, uint32_t n, float eps, uint32_t T,
                       cudaStream_t stream);
 

@@ -39,7 +39,7 @@ class GlobalPtrs(C.Structure):
 class CommPtrs(C.Structure):
     _fields_ = [("nRanks", u32), ("rank", u32), ("maxCtas", u32), ("slotStride", u32), ("arena", vp * 8),
                 ("slotsOff", u64), ("flagsOff", u64), ("candValOff", u64), ("candIdxOff", u64), ("candFlagOff", u64),
-                ("gatherOff", u64)]
+                ("gatherOff", u64), ("prefillSlotsOff", u64), ("prefillSlotStride", u32)]
 
 
 def lib() -> C.CDLL:

@@ -26,10 +26,12 @@ class ArenaLayout:
     cand_idx_off: int
     cand_flag_off: int
     gather_off: int
+    prefill_slots_off: int
+    prefill_slot_stride: int
     total: int
 
 
-def arena_layout(n_ranks: int, max_batch: int, dim: int, vocab_full: int) -> ArenaLayout:
+def arena_layout(n_ranks: int, max_batch: int, dim: int, vocab_full: int, max_prefill: int = 0) -> ArenaLayout:
     def align(x):
         return (x + 255) // 256 * 256
     off = 0
@@ -39,7 +41,8 @@ def arena_layout(n_ranks: int, max_batch: int, dim: int, vocab_full: int) -> Are
     ci = off; off = align(off + 64)
     cf = off; off = align(off + 64)
     gather = off; off = align(off + max_batch * vocab_full * 4)
-    return ArenaLayout(slots, flags, cv, ci, cf, gather, off)
+    pslots = off; off = align(off + 2 * n_ranks * max_prefill * dim * 8)
+    return ArenaLayout(slots, flags, cv, ci, cf, gather, pslots, max_prefill * dim, off)
 
 
 class Communicator:
@@ -86,7 +89,8 @@ class Communicator:
         arr = (C.c_void_p * 8)(*([C.c_void_p(p) for p in self.arena_ptrs] + [None] * (8 - len(self.arena_ptrs))))
         return cl.CommPtrs(nRanks=self.world_size, rank=self.rank, maxCtas=MAX_CTAS, slotStride=slot_stride, arena=arr,
                            slotsOff=L.slots_off, flagsOff=L.flags_off, candValOff=L.cand_val_off, candIdxOff=L.cand_idx_off,
-                           candFlagOff=L.cand_flag_off, gatherOff=L.gather_off)
+                           candFlagOff=L.cand_flag_off, gatherOff=L.gather_off, prefillSlotsOff=L.prefill_slots_off,
+                           prefillSlotStride=L.prefill_slot_stride)
 
     # ---- baseline collectives (NCCL) ----
     def all_reduce(self, t: torch.Tensor) -> torch.Tensor:

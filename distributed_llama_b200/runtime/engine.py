@@ -102,7 +102,7 @@ class Engine:
         self.comm = comm
         if comm is not None and comm.world_size > 1:
             from ..parallel.comm import arena_layout
-            comm.alloc_arena(arena_layout(comm.world_size, max_batch, h.dim, h.vocab_size))
+            comm.alloc_arena(arena_layout(comm.world_size, max_batch, h.dim, h.vocab_size, self.max_prefill))
             cp = comm.comm_ptrs(max_batch * h.dim)
             cl.check(self._lib.dl_engine_set_comm(self._h, C.byref(cp)), "engine_set_comm")
         self.use_tc_prefill = True
@@ -160,7 +160,11 @@ class Engine:
         tokens = list(tokens)
         if start_pos + len(tokens) > self.seq_len:
             raise ValueError("position beyond the context length")
-        tc_path = (self.comm is None or self.comm.world_size == 1) and self.w.header.n_experts == 0 and self.use_tc_prefill
+        hdr = self.w.header
+        tp = self.comm is not None and self.comm.world_size > 1
+        # tensor parallel: the fused GEMM + all-reduce kernel needs 256-wide K slices on every rank
+        tp_ok = (not tp) or ((self.w.n_heads * hdr.head_dim) % 256 == 0 and self.w.ff_dim % 256 == 0 and hdr.dim % 256 == 0)
+        tc_path = tp_ok and hdr.n_experts == 0 and self.use_tc_prefill
         i = 0
         while i < len(tokens):
             rem = len(tokens) - i

@@ -48,6 +48,10 @@ def main():
         eng3.enable_mega()
     eng3.prefill(prompt[:-1], 0, want_logits=False)
     toks_eager = eng3.decode_greedy(prompt[-1], len(prompt) - 1, 32, use_graph=False)
+    # tensor-core prefill under TP (fused GEMM + all-reduce) followed by a decode step
+    long_prompt = [(7 * i + 3) % 500 + 1 for i in range(45)]
+    eng4 = Engine(load_device_weights(mf, comm.rank, comm.world_size, moe_mode=moe_mode), comm=comm)
+    lg_pf = eng4.prefill(long_prompt, 0).clone()
     # every rank must have produced the same tokens
     t = torch.tensor(toks_graph, device="cuda")
     gathered = [torch.empty_like(t) for _ in range(comm.world_size)]
@@ -63,12 +67,16 @@ def main():
         ref_toks = single2.decode_greedy(prompt[-1], len(prompt) - 1, 32)
         oracle = OracleModel(mf, act_quant="q80", device="cuda")
         olg = oracle.forward(prompt, 0)
+        single3 = Engine(load_device_weights(mf, 0, 1))
+        ref_pf = single3.prefill(long_prompt, 0).clone()
+        e3 = (lg_pf - ref_pf).abs().max().item()
+        print(f"prefill(45 tok) max|tp - tp1| = {e3:.4g}")
         e1 = (lg - ref_lg).abs().max().item()
         e2 = (lg - olg).abs().max().item()
         n_agree = sum(a == b for a, b in zip(toks_graph, ref_toks))
         print(f"moe_mode={eng.w.moe_mode} tp={comm.world_size} max|tp - tp1|={e1:.4g} max|tp - oracle|={e2:.4g} greedy agree {n_agree}/32 "
               f"graph==eager {toks_graph == toks_eager} ranks agree {same_across_ranks}")
-        ok = e1 < 0.05 and e2 < 0.08 and toks_graph == toks_eager and same_across_ranks and n_agree >= 8
+        ok = e3 < 0.05 and e1 < 0.05 and e2 < 0.08 and toks_graph == toks_eager and same_across_ranks and n_agree >= 8
         print("mega" if mega else "multi-kernel", "decode path")
         print("TP_CHECK", "PASS" if ok else "FAIL")
     dist.barrier()
