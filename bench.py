@@ -137,8 +137,8 @@ def run_ours(args):
     t0 = time.time()
     sess = InferenceSession(model_path, tok_path, max_seq_len=args.max_seq_len, temperature=0.0, comm=comm)
     eng = sess.engine
-    if args.decode_path == "mega":
-        eng.enable_mega()
+    if args.decode_path == "multi":
+        eng.enable_mega(False)
     log(f"[bench] rank {rank}: weights on device in {time.time() - t0:.1f}s ({sess.weights.bytes_uploaded / 1e9:.2f} GB uploaded)")
 
     steps, warmup = args.steps, max(args.warmup, 3)
@@ -226,7 +226,7 @@ def run_ours(args):
             "vs_baseline": round(value / base, 2), "dtype": "q40 weights, q80 activations (int8 dp4a), bf16 KV, f32 accum",
             "data": "synthetic (random-init weights in .m layout, synthetic prompt)",
             "config": {"model": args.model, "global_batch": 1, "seq_len": args.prompt_len + steps, "prompt_len": args.prompt_len,
-                       "parallelism": f"tp{args.gpus}", "l2_policy": "weights per step (%.2f GB/GPU) >> 126 MB L2, no flush needed" % (weight_bytes / 1e9),
+                       "parallelism": f"tp{args.gpus}", "decode_path": "persistent megakernel" if eng.mega else "multi-kernel PDL chain", "l2_policy": "weights per step (%.2f GB/GPU) >> 126 MB L2, no flush needed" % (weight_bytes / 1e9),
                        "baseline_ref": "reference published Llama-2-7B q40 ms/token on %d x RPi 4B (report.pdf)" % args.gpus},
             "ttft_ms": round(ttft_ms, 3), "prefill_tokens_per_s": round(args.prompt_len / ttft_ms * 1e3, 1),
             "e2e": {"value": round(steps / e2e_ms * 1e3, 2), "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 4},
@@ -358,7 +358,7 @@ def main():
     ap.add_argument("--prompt-len", type=int, default=64)
     ap.add_argument("--max-seq-len", type=int, default=2048)
     ap.add_argument("--ref-timeout", type=int, default=1500)
-    ap.add_argument("--decode-path", default="multi", choices=["multi", "mega"], help="multi-kernel PDL chain or persistent megakernel")
+    ap.add_argument("--decode-path", default="mega", choices=["multi", "mega"], help="multi-kernel PDL chain or persistent megakernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

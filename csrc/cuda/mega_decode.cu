@@ -32,16 +32,14 @@ struct MegaSmem {
 };
 
 __device__ __forceinline__ void gridBarrier(unsigned int *ctr, unsigned int &target, int tid) {
-    consumerBarrier();
+    consumerBarrier();   // orders every consumer thread's global writes before thread 0's release below
     if (tid == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         target += gridDim.x;
         unsigned int v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         } while (v < target);
-        __threadfence();
     }
     consumerBarrier();
 }
@@ -51,7 +49,8 @@ __device__ __forceinline__ float4 ldcg4(const float4 *p) { return __ldcg(p); }
 // One GEMV phase on the consumer warps. `fillIdx` is the running fill counter shared (by construction) with the producer.
 template <int PRO, int EPI>
 __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, uint32_t d, uint32_t n, const float *in, const float *normW, float *out,
-                         uint32_t arParity, uint32_t &fillIdx, int tid) {
+                         uint32_t arParity, uint32_t &fillIdx, int tid, uint32_t &slot) {
+    auto stamp = [&]() { if (m.trace && blockIdx.x == 0 && tid == 0) m.trace[slot] = globalTimerNs(); slot++; };
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t nblk = n / 32, nseg = (nblk + 31) / 32;
     const uint32_t rowQsBytes = nblk * 16;
@@ -64,26 +63,32 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, uint32_t d, uint
     uint4 *planeA = sm.planeA, *planeB = sm.planeB;
     float *dxs = sm.dxs, *dx8 = sm.dx8, *partial = sm.partial, *red = sm.red;
 
-    // ---- prologue: (rmsnorm) + q80 quantisation of the activation vector ----
+    // ---- prologue: (rmsnorm) + q80 quantisation of the activation vector (one pass: the vector stays in registers) ----
     {
         const uint32_t nVec = n / 4;
         const float4 *x4 = reinterpret_cast<const float4 *>(in);
+        constexpr int kMaxVec = 8;                       // 8 float4 x 512 threads = 16384 elements
+        float4 xv[kMaxVec];
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxVec; k++) {
+            const uint32_t i = k * kConsumerThreads + tid;
+            xv[k] = i < nVec ? ldcg4(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ss += xv[k].x * xv[k].x + xv[k].y * xv[k].y + xv[k].z * xv[k].z + xv[k].w * xv[k].w;
+        }
         float inv = 1.f;
         if (PRO == PRO_RMSNORM_) {
-            float ss = 0.f;
-            for (uint32_t i = tid; i < nVec; i += kConsumerThreads) {
-                const float4 v = ldcg4(x4 + i);
-                ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-            }
             ss = consumerSum(ss, red);
             inv = rsqrtf(ss / (float)n + m.eps);
         }
         uint8_t *pa = reinterpret_cast<uint8_t *>(planeA);
         uint8_t *pb = reinterpret_cast<uint8_t *>(planeB);
-        for (uint32_t base = 0; base < nVec; base += kConsumerThreads) {
-            const uint32_t i = base + tid;
+#pragma unroll
+        for (int k = 0; k < kMaxVec; k++) {
+            const uint32_t i = k * kConsumerThreads + tid;
+            if (k * kConsumerThreads >= nVec) break;     // block-uniform
             const bool act = i < nVec;
-            float4 v = act ? ldcg4(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 v = xv[k];
             if (PRO == PRO_RMSNORM_ && act) {
                 const float4 w = reinterpret_cast<const float4 *>(normW)[i];
                 v.x = w.x * (v.x * inv); v.y = w.y * (v.y * inv); v.z = w.z * (v.z * inv); v.w = w.w * (v.w * inv);
@@ -101,9 +106,9 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, uint32_t d, uint
             qsum += __shfl_xor_sync(0xffffffffu, qsum, 2);
             qsum += __shfl_xor_sync(0xffffffffu, qsum, 4);
             if (act) {
-                const uint32_t b = i >> 3, sub = i & 7, k = sub >> 1, odd = sub & 1;
-                uint8_t *wa = pa + (size_t)b * 16 + k * 4 + odd;
-                uint8_t *wb = pb + (size_t)b * 16 + k * 4 + odd;
+                const uint32_t b = i >> 3, sub = i & 7, kk = sub >> 1, odd = sub & 1;
+                uint8_t *wa = pa + (size_t)b * 16 + kk * 4 + odd;
+                uint8_t *wb = pb + (size_t)b * 16 + kk * 4 + odd;
                 wa[0] = (uint8_t)(int8_t)q0; wa[2] = (uint8_t)(int8_t)q1;
                 wb[0] = (uint8_t)(int8_t)q2; wb[2] = (uint8_t)(int8_t)q3;
                 if (sub == 0) {
@@ -115,6 +120,7 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, uint32_t d, uint
         }
     }
     consumerBarrier();
+    stamp();   // prologue done
 
     // ---- main loop over this phase's fills ----
     for (uint32_t f = 0; f < nFills; f++, fillIdx++) {
@@ -131,10 +137,12 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, uint32_t d, uint
         mbarWait(&sm.fullBar[st], (fillIdx / m.nStages) & 1);
         uint32_t g = firstStep / nseg, seg = firstStep - g * nseg;
         const uint32_t gInc = kConsumerWarps / nseg, segInc = kConsumerWarps - gInc * nseg;
-        for (uint32_t s = firstStep; s < nSteps; s += kConsumerWarps) {
-            const uint32_t blk = seg * 32 + lane;
-            const uint32_t rl = g * kRowsPerStep;
-            float acc[kRowsPerStep] = {0.f, 0.f, 0.f, 0.f};
+        // two steps are processed together (independent dependency chains -> the LDS/IDP/SHFL latencies overlap)
+        auto stepDot = [&](uint32_t g_, uint32_t seg_, float (&acc)[kRowsPerStep]) {
+            const uint32_t blk = seg_ * 32 + lane;
+            const uint32_t rl = g_ * kRowsPerStep;
+#pragma unroll
+            for (int r = 0; r < kRowsPerStep; r++) acc[r] = 0.f;
             if (blk < nblk) {
                 const uint4 A = planeA[blk], B = planeB[blk];
                 const float dxv = dxs[blk], dx8v = dx8[blk];
@@ -152,19 +160,43 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, uint32_t d, uint
                     acc[r] = dw * (dxv * (float)(lo + (hi >> 4)) - dx8v);
                 }
             }
-            const float v = reduce4(acc[0], acc[1], acc[2], acc[3], lane);
+        };
+        auto stepStore = [&](uint32_t g_, uint32_t seg_, float v) {
+            const uint32_t rl = g_ * kRowsPerStep;
             if ((lane & 7) == 0) {
                 const uint32_t r = lane >> 3;
-                if (rl + r < rows) partial[(r0 + rl + r) * nseg + seg] = v;
+                if (rl + r < rows) partial[(r0 + rl + r) * nseg + seg_] = v;
             }
-            g += gInc;
-            seg += segInc;
-            if (seg >= nseg) { seg -= nseg; g++; }
+        };
+        auto advance = [&](uint32_t &g_, uint32_t &seg_) {
+            g_ += gInc;
+            seg_ += segInc;
+            if (seg_ >= nseg) { seg_ -= nseg; g_++; }
+        };
+        uint32_t s = firstStep;
+        for (; s + kConsumerWarps < nSteps; s += 2 * kConsumerWarps) {
+            uint32_t g2 = g, seg2 = seg;
+            advance(g2, seg2);
+            float a0[kRowsPerStep], a1[kRowsPerStep];
+            stepDot(g, seg, a0);
+            stepDot(g2, seg2, a1);
+            const float v0 = reduce4(a0[0], a0[1], a0[2], a0[3], lane);
+            const float v1 = reduce4(a1[0], a1[1], a1[2], a1[3], lane);
+            stepStore(g, seg, v0);
+            stepStore(g2, seg2, v1);
+            g = g2; seg = seg2;
+            advance(g, seg);
+        }
+        if (s < nSteps) {
+            float a0[kRowsPerStep];
+            stepDot(g, seg, a0);
+            stepStore(g, seg, reduce4(a0[0], a0[1], a0[2], a0[3], lane));
         }
         __syncwarp();
         if (lane == 0) mbarArrive(&sm.emptyBar[st]);
     }
     consumerBarrier();
+    stamp();   // main loop done
 
     // ---- epilogue ----
     auto rowSum = [&](uint32_t r) {
@@ -553,26 +585,37 @@ __global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_
     if (p < 0) p = 0;
     if ((uint32_t)p >= m.seqLen) p = m.seqLen - 1;
     gridBarrier(m.gridCounter, barTarget, tid);
+    auto prefetchVec = [&](const float *p) {   // norm weights are constants: pull them towards L2 ahead of their phase
+        for (uint32_t i = (blockIdx.x * kConsumerThreads + tid) * 32; i < m.dim; i += gridDim.x * kConsumerThreads * 32)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i));
+    };
     for (uint32_t l = 0; l < m.nLayers; l++) {
         const MegaLayer &L = m.layers[l];
+        prefetchVec(L.norm1);
+        prefetchVec(l + 1 < m.nLayers ? m.layers[l + 1].norm0 : m.finalNorm);
         stamp();
-        megaGemv<PRO_RMSNORM_, EPI_STORE_>(m, sm, qkvDim, m.dim, m.x, L.norm0, m.qkv, 0, fillIdx, tid);
+        megaGemv<PRO_RMSNORM_, EPI_STORE_>(m, sm, qkvDim, m.dim, m.x, L.norm0, m.qkv, 0, fillIdx, tid, slot);
+        stamp();
         gridBarrier(m.gridCounter, barTarget, tid);
         stamp();
         megaAttention<HD>(m, sm, L, p, tid);
+        stamp();
         gridBarrier(m.gridCounter, barTarget, tid);
         stamp();
-        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.dim, qDim, m.z, nullptr, m.x, 0, fillIdx, tid);
+        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.dim, qDim, m.z, nullptr, m.x, 0, fillIdx, tid, slot);
+        stamp();
         gridBarrier(m.gridCounter, barTarget, tid);
         stamp();
-        megaGemv<PRO_RMSNORM_, EPI_SWIGLU_>(m, sm, 2 * m.ffDim, m.dim, m.x, L.norm1, m.h, 0, fillIdx, tid);
+        megaGemv<PRO_RMSNORM_, EPI_SWIGLU_>(m, sm, 2 * m.ffDim, m.dim, m.x, L.norm1, m.h, 0, fillIdx, tid, slot);
+        stamp();
         gridBarrier(m.gridCounter, barTarget, tid);
         stamp();
-        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.dim, m.ffDim, m.h, nullptr, m.x, 1, fillIdx, tid);
+        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.dim, m.ffDim, m.h, nullptr, m.x, 1, fillIdx, tid, slot);
+        stamp();
         gridBarrier(m.gridCounter, barTarget, tid);
     }
     stamp();
-    megaGemv<PRO_RMSNORM_, EPI_ARGMAX_>(m, sm, m.vocab, m.dim, m.x, m.finalNorm, m.logits, 0, fillIdx, tid);
+    megaGemv<PRO_RMSNORM_, EPI_ARGMAX_>(m, sm, m.vocab, m.dim, m.x, m.finalNorm, m.logits, 0, fillIdx, tid, slot);
     stamp();
 }
 
@@ -586,6 +629,7 @@ int launchMegaDecode(MegaArgs m, int numSms, cudaStream_t stream) {
         if (n % 128) return 1;
         if (n > maxN) maxN = n;
     }
+    if (maxN > 8 * kConsumerThreads * 4) return 1;   // the activation vector is held in registers during the prologue
     const uint32_t grid = (uint32_t)numSms;
     // partial buffer: rows of the largest tile x segments; also hosts the attention scratch (16 x HD + 32 floats)
     const uint32_t ds[5] = {qDim + 2 * m.nKvHeads * m.headDim, m.dim, 2 * m.ffDim, m.dim, m.vocab};

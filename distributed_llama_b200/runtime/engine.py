@@ -8,6 +8,7 @@ Plays the role of the reference's RootLlmInference (src/app.cpp:168-208): setBat
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -107,6 +108,8 @@ class Engine:
             cl.check(self._lib.dl_engine_set_comm(self._h, C.byref(cp)), "engine_set_comm")
         self.use_tc_prefill = True
         self.mega = False
+        if h.n_experts == 0 and os.environ.get("DL_NO_MEGA") is None:
+            self.enable_mega(True)     # persistent decode kernel by default; the engine falls back per call if a shape is unsupported
         self.tc_min_tokens = 9          # shorter chunks stay on the GEMV path
         self._graph_ready = False
         self._stage_tok = torch.zeros(max_batch, dtype=torch.int32).pin_memory()
@@ -214,6 +217,8 @@ class Engine:
 
     @property
     def launches_per_decode_step(self) -> int:
+        if self.mega:
+            return 1                # one persistent kernel per token (plus a 4-byte memset node)
         if self.w.header.n_experts > 0:
             return self.w.header.n_layers * 6 + 2
         return self.w.header.n_layers * 5 + 2   # embedding + 5 fused kernels per layer + logits/arg-max

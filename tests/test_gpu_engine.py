@@ -81,6 +81,7 @@ def test_tensor_core_prefill_matches_oracle(tmp_models, name):
 def test_persistent_decode_kernel(tmp_models, name):
     """The one-launch-per-token megakernel must reproduce the multi-kernel path (logits close, greedy tokens equal)."""
     mf, eng, oracle = _setup(tmp_models, name)
+    eng.enable_mega(False)          # reference: the multi-kernel PDL chain
     prompt = [3, 17, 250, 9, 44, 101, 7]
     eng.prefill(prompt[:-1], 0, want_logits=False)
     ref_toks = eng.decode_greedy(prompt[-1], len(prompt) - 1, 40)
@@ -89,6 +90,7 @@ def test_persistent_decode_kernel(tmp_models, name):
     eng_m.prefill(prompt[:-1], 0, want_logits=False)
     lg_m = eng_m.step(prompt[-1], len(prompt) - 1).clone()
     eng_c = _setup(tmp_models, name)[1]
+    eng_c.enable_mega(False)
     eng_c.prefill(prompt[:-1], 0, want_logits=False)
     lg_c = eng_c.step(prompt[-1], len(prompt) - 1).clone()
     assert (lg_m - lg_c).abs().max().item() < 2e-3

@@ -35,9 +35,16 @@ if rank != 0:
 st = eng.trace_buf.cpu().numpy().reshape(-1)
 st = st[st != 0].astype(np.float64)
 st = (st - st[0]) / 1e3
-names = ["embed"] + ["qkv", "attn", "wo", "w13", "w2"] * eng.w.header.n_layers + ["logits", "end"]
+L = eng.w.header.n_layers
+names = ["embed"]
+for _ in range(L):
+    names += ["qkv.pro", "qkv.main", "qkv.epi", "qkv.bar", "attn.run", "attn.bar", "wo.pro", "wo.main", "wo.epi", "wo.bar",
+              "w13.pro", "w13.main", "w13.epi", "w13.bar", "w2.pro", "w2.main", "w2.epi", "w2.bar"]
+names += ["logits.pro", "logits.main", "logits.epi"]
 dur = np.diff(st)
-print("total step us:", st[-1])
-for nm in ["embed", "qkv", "attn", "wo", "w13", "w2", "logits"]:
-    d = [dur[i] for i in range(len(dur)) if names[i] == nm]
-    print(f"{nm:7s} n={len(d):3d} mean={np.mean(d):7.2f} us  min={np.min(d):7.2f} max={np.max(d):7.2f}")
+print("total step us:", st[-1], "stamps", len(st), "expected", len(names) + 1)
+agg = {}
+for i, d in enumerate(dur):
+    agg.setdefault(names[i] if i < len(names) else "?", []).append(d)
+for nm, d in agg.items():
+    print(f"{nm:12s} n={len(d):3d} mean={np.mean(d):7.2f} us  min={np.min(d):7.2f} max={np.max(d):7.2f}")
