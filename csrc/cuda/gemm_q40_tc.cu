@@ -38,6 +38,9 @@ struct GemmArgs {
     void *out;
     uint32_t outStride;   // elements between tokens
     uint32_t stages, tmemCols;
+    uint32_t splitK;       // TMA-staged variant: K is cut into splitK ranges handled by different CTAs (work item = tile x split)
+    float *splitScratch;   // [splitK][T][d] f32 partial accumulators
+    unsigned int *splitCounters;   // [nTilesM * 4], zero-initialised, self-resetting (one per 32-row quarter of a tile)
     ArArgs ar;             // GEPI_RESIDUAL_AR: tensor-parallel all-reduce fused into the epilogue (LL words over peer memory)
     uint32_t rawStages;    // TMA-staged variant: depth of the raw q40 ring (2 or 3)
     uint32_t debugFlags;   // bit0: skip the proxy fence, bit1: skip the A-tile stores (timing experiments only)
@@ -311,6 +314,10 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
     const uint32_t nkb = a.n / kGmBlockK;
     const uint32_t nkq = (a.n + kGmRawK - 1) / kGmRawK;
     const uint32_t nTilesM = (a.d + kGmBlockM - 1) / kGmBlockM;
+    const uint32_t splitK = a.splitK;
+    const uint32_t nItems = nTilesM * splitK;
+    // work item -> (row tile, K range in 256-wide raw chunks); consecutive items share a tile
+    auto kqBegin = [&](uint32_t ks) { return (uint32_t)(((uint64_t)ks * nkq) / splitK); };
 
     pdlLaunchDependents();
     if (tid == 0) {
@@ -341,8 +348,9 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
         // ===================== raw weight producer (weights are constants: no dependency wait) =====================
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x) {
-                for (uint32_t kq = 0; kq < nkq; kq++, it++) {
+            for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
+                const uint32_t tile = item / splitK, ks = item - tile * splitK;
+                for (uint32_t kq = kqBegin(ks); kq < kqBegin(ks + 1); kq++, it++) {
                     const uint32_t rs = it % a.rawStages, ph = (it / a.rawStages) & 1;
                     gmBarWait(&rawEmpty[rs], ph ^ 1);
                     uint8_t *dst = rawBase + (size_t)rs * kGmRawStageBytes;
@@ -357,8 +365,9 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
         pdlWait();
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x) {
-                for (uint32_t kb = 0; kb < nkb; kb++, it++) {
+            for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
+                const uint32_t ks = item % splitK;
+                for (uint32_t kb = kqBegin(ks) * 4; kb < min(kqBegin(ks + 1) * 4, nkb); kb++, it++) {
                     const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
                     gmBarWait(&emptyBar[s], ph ^ 1);
                     gmBarExpectTx(&fullBar[s], bTileBytes);
@@ -370,12 +379,14 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
         // ===================== MMA issuer =====================
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((nTile >> 3) << 17) | ((uint32_t)(kGmBlockM >> 4) << 24);
         uint32_t it = 0, tcount = 0;
-        for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x, tcount++) {
+        for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x, tcount++) {
+            const uint32_t ks = item % splitK;
+            const uint32_t kb0 = kqBegin(ks) * 4, kb1 = min(kqBegin(ks + 1) * 4, nkb);
             const uint32_t acc = tcount & 1, accPh = (tcount >> 1) & 1;
             gmBarWait(&tmemEmpty[acc], accPh ^ 1);
             tcFenceAfter();
             const uint32_t tmemD = tmemBase + acc * nTile;
-            for (uint32_t kb = 0; kb < nkb; kb++, it++) {
+            for (uint32_t kb = kb0; kb < kb1; kb++, it++) {
                 const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
                 gmBarWait(&fullBar[s], ph);
                 tcFenceAfter();
@@ -384,9 +395,9 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                     const uint64_t descA = makeSmemDesc(aAddr);
                     const uint64_t descB = makeSmemDesc(aAddr + kGmATileBytes);
 #pragma unroll
-                    for (uint32_t k = 0; k < kGmBlockK / 16; k++) umma(tmemD, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (uint32_t k = 0; k < kGmBlockK / 16; k++) umma(tmemD, descA + 2 * k, descB + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     ummaCommit(&emptyBar[s]);
-                    if (kb == nkb - 1) ummaCommit(&tmemFull[acc]);
+                    if (kb == kb1 - 1) ummaCommit(&tmemFull[acc]);
                 }
                 __syncwarp();
             }
@@ -396,12 +407,64 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
         pdlWait();   // the residual stream is read-modify-written
         const uint32_t q = warp - 4;
         uint32_t tcount = 0;
-        for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x, tcount++) {
+        for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x, tcount++) {
+            const uint32_t tile = item / splitK, ks = item - tile * splitK;
             const uint32_t acc = tcount & 1, accPh = (tcount >> 1) & 1;
             gmBarWait(&tmemFull[acc], accPh);
             tcFenceAfter();
             const uint32_t f = tile * kGmBlockM + q * 32 + lane;
             const bool fOk = f < a.d;
+            if (splitK > 1) {
+                // ---- split-K: park the partial accumulator, the last split of this 32-row quarter reduces in fixed order ----
+                float *mineS = a.splitScratch + (size_t)ks * a.T * a.d;
+                for (uint32_t c0 = 0; c0 < nTile; c0 += 16) {
+                    uint32_t r[16];
+                    tmemLoad16(tmemBase + ((q * 32u) << 16) + acc * nTile + c0, r);
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if (c0 + j < a.T && fOk) mineS[(size_t)(c0 + j) * a.d + f] = __uint_as_float(r[j]);
+                }
+                tcFenceBefore();
+                __syncwarp();
+                if (lane == 0) gmBarArrive(&tmemEmpty[acc]);
+                __threadfence();
+                __syncwarp();
+                unsigned int prev = 0;
+                if (lane == 0) prev = atomicAdd(&a.splitCounters[tile * 4 + q], 1u);
+                prev = __shfl_sync(0xffffffffu, prev, 0);
+                if (prev != splitK - 1) continue;
+                if (lane == 0) a.splitCounters[tile * 4 + q] = 0;
+                __threadfence();
+                for (uint32_t tok0 = 0; tok0 < a.T; tok0 += 4) {
+                    // 4 tokens x up to 8 splits (+ 4 residual values) are loaded before any arithmetic: ~36 loads in flight per thread
+                    float part[4][8], res[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const bool ok = fOk && tok0 + j < a.T;
+#pragma unroll
+                        for (int k2 = 0; k2 < 8; k2++)
+                            part[j][k2] = (ok && (uint32_t)k2 < splitK) ? __ldcg(a.splitScratch + ((size_t)k2 * a.T + tok0 + j) * a.d + f) : 0.f;
+                        res[j] = (EPI == GEPI_RESIDUAL && ok) ? __ldcg(reinterpret_cast<const float *>(a.out) + (size_t)(tok0 + j) * a.outStride + f) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t tok = tok0 + j;
+                        float v = 0.f;
+#pragma unroll
+                        for (int k2 = 0; k2 < 8; k2++) v += part[j][k2];          // fixed order -> deterministic
+                        if (EPI == GEPI_SWIGLU_BF16) {
+                            const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+                            if (fOk && tok < a.T && !(lane & 1))
+                                reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(siluf(v) * other);
+                        } else if (fOk && tok < a.T) {
+                            if (EPI == GEPI_STORE_F32) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v;
+                            if (EPI == GEPI_RESIDUAL) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = res[j] + v;
+                            if (EPI == GEPI_STORE_BF16) reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + f] = __float2bfloat16_rn(v);
+                        }
+                    }
+                }
+                continue;
+            }
             if (EPI == GEPI_RESIDUAL_AR) {
                 // ---- GEMM + all-reduce in one kernel: the accumulator tile goes from TMEM straight into LL words of
                 // every rank's slot[myRank] (NVLink peer stores, 256 B per warp store); after the TMEM buffer is released
@@ -497,8 +560,9 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
         const uint32_t j = (uint32_t)tid - 256u - grp * 64u;       // 0..63: rows j and j + 64
         const __nv_bfloat162 off = __floats2bfloat162_rn(136.f, 136.f);
         uint32_t itR = 0;
-        for (uint32_t tile = blockIdx.x; tile < nTilesM; tile += gridDim.x) {
-            for (uint32_t kq = 0; kq < nkq; kq++, itR++) {
+        for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
+            const uint32_t ks = item % splitK;
+            for (uint32_t kq = kqBegin(ks); kq < kqBegin(ks + 1); kq++, itR++) {
                 const uint32_t rs = itR % a.rawStages, rph = (itR / a.rawStages) & 1;
                 gmBarWait(&rawFull[rs], rph);
                 const uint8_t *rbase = rawBase + (size_t)rs * kGmRawStageBytes;
@@ -612,6 +676,10 @@ static bool encode2d(EncodeTiledFn enc, CUtensorMap *map, CUtensorMapDataType ty
 }
 
 // act: bf16 [T][n] row-major (row stride actStride elements). variant: 0 auto, 1 register-prefetch dequant, 2 TMA-staged raw weights.
+static float *gSplitScratch = nullptr;
+static unsigned int *gSplitCounters = nullptr;
+static size_t gSplitScratchBytes = 0;
+
 int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T,
                void *out, uint32_t outStride, int numSms, cudaStream_t stream, bool pdl, int variant, const ArArgs *ar) {
     if (T == 0 || T > 256 || n % kGmBlockK || d % 2) return -1;
@@ -661,7 +729,29 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
         if (!encode2d(enc, &mapS, CU_TENSOR_MAP_DATA_TYPE_UINT8, scales, n / 16, d, n / 16, 16, kGmBlockM, CU_TENSOR_MAP_SWIZZLE_NONE)) return -8;
     }
     const uint32_t nTilesM = (d + kGmBlockM - 1) / kGmBlockM;
-    const int grid = (int)(nTilesM < (uint32_t)numSms ? nTilesM : (uint32_t)numSms);
+    a.splitK = 1;
+    if (tma && epi != GEPI_RESIDUAL_AR) {
+        // small-d matrices (qkv, wo, w2) leave most SMs idle with one CTA per 128-row tile: cut K so that ~all SMs get an item
+        const uint32_t nkq = n / 256;
+        uint32_t sk = (uint32_t)numSms / nTilesM;
+        if (sk > 8) sk = 8;
+        if (sk > nkq / 8) sk = nkq / 8;   // every split keeps >= 8 raw chunks (2048 of K): below that the scratch round trip costs more than it saves
+        if (sk >= 2) {
+            const size_t need = (size_t)sk * T * d * sizeof(float);
+            if (need > gSplitScratchBytes) {
+                if (gSplitScratch) cudaFree(gSplitScratch);
+                DL_CUDA_CHECK(cudaMalloc(&gSplitScratch, need));
+                gSplitScratchBytes = need;
+            }
+            if (!gSplitCounters) {
+                DL_CUDA_CHECK(cudaMalloc(&gSplitCounters, 4096 * sizeof(unsigned int)));
+                DL_CUDA_CHECK(cudaMemset(gSplitCounters, 0, 4096 * sizeof(unsigned int)));
+            }
+            if (nTilesM * 4 <= 4096) { a.splitK = sk; a.splitScratch = gSplitScratch; a.splitCounters = gSplitCounters; }
+        }
+    }
+    const uint32_t nItems = nTilesM * a.splitK;
+    const int grid = (int)(nItems < (uint32_t)numSms ? nItems : (uint32_t)numSms);
     const CUtensorMap *pq = tma ? &mapQ : nullptr, *ps = tma ? &mapS : nullptr;
     switch (epi) {
         case GEPI_STORE_F32: return launchGemm<GEPI_STORE_F32>(mapB, pq, ps, a, grid, smemBytes, stream, pdl);

@@ -87,6 +87,7 @@ PRESETS: Dict[str, ModelConfig] = {
     "tiny-llama": ModelConfig("tiny-llama", ARCH_LLAMA, 256, 512, 2, 4, 2, 512, 256, rope_theta=10000),
     "tiny-llama31": _llama3("tiny-llama31", 512, 1024, 3, 8, 4, seq=512, vocab=512),
     "tiny-llama-tp8": _llama3("tiny-llama-tp8", 1024, 2048, 2, 16, 8, seq=512, vocab=1024),
+    "tiny-llama-kvrep": _llama3("tiny-llama-kvrep", 512, 1024, 2, 8, 2, seq=512, vocab=512),
     "tiny-qwen3": ModelConfig("tiny-qwen3", ARCH_QWEN3, 256, 512, 2, 4, 2, 512, 256, head_dim=128,
                               rope_theta=1000000, norm_epsilon=6),
     "tiny-qwen3-moe": ModelConfig("tiny-qwen3-moe", ARCH_QWEN3_MOE, 256, 512, 2, 4, 2, 512, 256, head_dim=128,

@@ -105,10 +105,19 @@ def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="
     ep = h.n_experts > 0 and moe_mode == "ep" and n_ranks > 1
     if ep and h.n_experts % n_ranks:
         raise ValueError("nExperts must be divisible by the number of ranks for expert parallelism")
-    if h.n_heads % n_ranks or h.n_kv_heads % n_ranks or (not ep and h.ff_dim % n_ranks) or h.vocab_size % n_ranks:
+    # KV-head replication: with more ranks than KV heads (the reference refuses this, src/app.cpp:236-238) groups of
+    # nRanks/nKvHeads ranks share one KV head; every rank still owns a distinct set of query heads of that group.
+    kv_rep = 1
+    if n_ranks > h.n_kv_heads:
+        if n_ranks % h.n_kv_heads or (h.n_heads // h.n_kv_heads) % (n_ranks // h.n_kv_heads):
+            raise ValueError("nRanks must be a multiple of nKvHeads that divides the query heads of a KV group")
+        kv_rep = n_ranks // h.n_kv_heads
+    if h.n_heads % n_ranks or (kv_rep == 1 and h.n_kv_heads % n_ranks) or (not ep and h.ff_dim % n_ranks) or h.vocab_size % n_ranks:
         raise ValueError("nHeads, nKvHeads, ffDim and vocabSize must be divisible by the number of ranks")
     hd = h.head_dim
-    nh, nkv = h.n_heads // n_ranks, h.n_kv_heads // n_ranks
+    nh, nkv = h.n_heads // n_ranks, (1 if kv_rep > 1 else h.n_kv_heads // n_ranks)
+    kv_rank = rank // kv_rep       # which KV slice this rank reads
+    kv_ranks = n_ranks // kv_rep   # number of distinct KV slices
     q0, kv0, ff0, v0 = nh * hd, nkv * hd, (h.ff_dim if ep else h.ff_dim // n_ranks), h.vocab_size // n_ranks
     if (q0 % 32) or (ff0 % 32):
         raise ValueError("column slices must cover whole 32-element quant blocks")
@@ -141,8 +150,8 @@ def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="
     for l in range(h.n_layers):
         qkv = DeviceQ40.empty(q0 + 2 * kv0, dim, device)
         row_sliced("block_matmul_q", l, 0, qkv, q0, head_dim=hd if neox else 0)
-        row_sliced("block_matmul_k", l, 0, qkv, kv0, dst_off=q0, head_dim=hd if neox else 0)
-        row_sliced("block_matmul_v", l, 0, qkv, kv0, dst_off=q0 + kv0)
+        row_sliced("block_matmul_k", l, 0, qkv, kv0, dst_off=q0, head_dim=hd if neox else 0, slice_rank=kv_rank)
+        row_sliced("block_matmul_v", l, 0, qkv, kv0, dst_off=q0 + kv0, slice_rank=kv_rank)
         wo = DeviceQ40.empty(dim, q0, device)
         col_sliced("block_matmul_wo", l, 0, wo, q0)
         w13 = DeviceQ40.empty(2 * ff0, dim, device, lead=n_local)

@@ -28,3 +28,34 @@ def test_moe_tensor_and_expert_parallel(mode):
            "--master-port", "29633", os.path.join(ROOT, "tools", "tp_check.py"), "tiny-qwen3-moe", mode]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert "TP_CHECK PASS" in r.stdout and f"moe_mode={mode}" in r.stdout, r.stdout[-3000:]
+
+
+def test_kv_head_replication_more_ranks_than_kv_heads():
+    """4 ranks, 2 KV heads: pairs of ranks share a KV head (the reference cannot run this configuration)."""
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+           "--master-port", "29644", os.path.join(ROOT, "tools", "tp_check.py"), "tiny-llama-kvrep"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert "TP_CHECK PASS" in r.stdout, r.stdout[-3000:]
+
+
+def test_dllama_cli_spawns_ranks():
+    """`dllama inference --gpus 2` (root + one worker process) prints the same continuation as the single-GPU run."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import tempfile
+    from distributed_llama_b200.models.config import get_config
+    from distributed_llama_b200.models.synthetic import write_synthetic_model, write_synthetic_tokenizer
+    with tempfile.TemporaryDirectory() as d:
+        m, t = os.path.join(d, "m.m"), os.path.join(d, "t.t")
+        write_synthetic_model(m, get_config("tiny-llama31"), seed=5)
+        write_synthetic_tokenizer(t, 512)
+        outs = []
+        for extra in ([], ["--gpus", "2"]):
+            r = subprocess.run([os.path.join(ROOT, "dllama"), "inference", "--model", m, "--tokenizer", t, "--buffer-float-type", "q80",
+                                "--prompt", "Hello world, the model", "--steps", "20", "--temperature", "0"] + extra,
+                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout[-2000:]
+            outs.append([ln.split("|")[-1] for ln in r.stdout.splitlines() if "🔶 Pred" in ln])
+        assert outs[0] == outs[1] and len(outs[0]) >= 10
