@@ -381,6 +381,56 @@ DL_EXPORT int dl_engine_forward(void *h, int nb, int logitsMode, int greedyAdvan
     return dl::engineForward(*(Engine *)h, nb, logitsMode, greedyAdvance != 0, stream);
 }
 
+// NCCL-baseline building blocks (decode path, nb tokens): the same kernels, but the tensor-parallel partial products are
+// *stored* into `ybuf` instead of being all-reduced in the epilogue; the caller all-reduces ybuf with NCCL and adds it to x.
+//   part 0: embedding              part 1: QKV + attention + WO -> ybuf
+//   part 2: W1|W3 + W2 -> ybuf     part 3: logits (local vocabulary slice)
+DL_EXPORT int dl_engine_forward_part(void *h, int nb, uint32_t layer, int part, float *ybuf, cudaStream_t stream) {
+    Engine &e = *(Engine *)h;
+    const dl::EngineConfig &c = e.cfg;
+    const uint32_t qDim = c.nHeads * c.headDim, kvDim = c.nKvHeads * c.headDim, qkvDim = qDim + 2 * kvDim;
+    if (part == 0) return dl::launchEmbedding(e.g.embedding, e.g.tokens, e.g.x, c.dim, c.dim, e.g.vocabFull, nb, stream);
+    if (part == 3) {
+        dl::GemvArgs a{};
+        a.qs = (const uint32_t *)e.g.wclsQs; a.scales = (const __half *)e.g.wclsSc; a.d = c.vocab; a.n = c.dim;
+        a.normW = e.g.finalNorm; a.eps = c.eps; a.inStride = c.dim; a.outStride = c.vocab; a.out = e.g.logits;
+        a.in = e.g.x + (size_t)(nb - 1) * c.dim;
+        return dl::gemvQ40Auto(dl::PRO_RMSNORM_, dl::EPI_STORE_, 1, a, c.numSms, stream, false);
+    }
+    if (layer >= c.nLayers || c.nExperts > 0) return -1;
+    const dl::LayerPtrs &L = e.layers[layer];
+    dl::GemvArgs a{};
+    if (part == 1) {
+        a.qs = (const uint32_t *)L.qkvQs; a.scales = (const __half *)L.qkvSc; a.d = qkvDim; a.n = c.dim;
+        a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm0; a.eps = c.eps; a.out = e.g.qkv; a.outStride = qkvDim;
+        DL_TRY(dl::gemvQ40Auto(dl::PRO_RMSNORM_, dl::EPI_STORE_, nb, a, c.numSms, stream, false));
+        dl::RopeKvArgs r{};
+        r.qkv = e.g.qkv; r.qkvStride = qkvDim; r.pos = e.g.pos; r.rope = e.g.rope; r.qNorm = L.qNorm; r.kNorm = L.kNorm;
+        r.eps = c.eps; r.nHeads = c.nHeads; r.nKvHeads = c.nKvHeads; r.headDim = c.headDim; r.seqLen = c.seqLen;
+        r.kCache = (__nv_bfloat16 *)L.kCache; r.vCache = (__nv_bfloat16 *)L.vCache;
+        DL_TRY(dl::launchRopeKv(r, nb, stream, false));
+        dl::AttnArgs t{};
+        t.qkv = e.g.qkv; t.qkvStride = qkvDim; t.pos = e.g.pos; t.kCache = r.kCache; t.vCache = r.vCache;
+        t.nHeads = c.nHeads; t.nKvHeads = c.nKvHeads; t.headDim = c.headDim; t.seqLen = c.seqLen; t.nSplits = c.nSplits;
+        t.partial = e.g.attnPartial; t.counters = e.g.attnCounters; t.out = e.g.z; t.outStride = qDim;
+        DL_TRY(dl::launchAttnDecode(t, nb, stream, false));
+        a = dl::GemvArgs{};
+        a.qs = (const uint32_t *)L.woQs; a.scales = (const __half *)L.woSc; a.d = c.dim; a.n = qDim;
+        a.in = e.g.z; a.inStride = qDim; a.out = ybuf; a.outStride = c.dim;
+        return dl::gemvQ40Auto(dl::PRO_PLAIN_, dl::EPI_STORE_, nb, a, c.numSms, stream, false);
+    }
+    if (part == 2) {
+        a.qs = (const uint32_t *)L.w13Qs; a.scales = (const __half *)L.w13Sc; a.d = 2 * c.ffDim; a.n = c.dim;
+        a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm1; a.eps = c.eps; a.out = e.g.h; a.outStride = c.ffDim;
+        DL_TRY(dl::gemvQ40Auto(dl::PRO_RMSNORM_, dl::EPI_SWIGLU_, nb, a, c.numSms, stream, false));
+        a = dl::GemvArgs{};
+        a.qs = (const uint32_t *)L.w2Qs; a.scales = (const __half *)L.w2Sc; a.d = c.dim; a.n = c.ffDim;
+        a.in = e.g.h; a.inStride = c.ffDim; a.out = ybuf; a.outStride = c.dim;
+        return dl::gemvQ40Auto(dl::PRO_PLAIN_, dl::EPI_STORE_, nb, a, c.numSms, stream, false);
+    }
+    return -2;
+}
+
 DL_EXPORT int dl_engine_prefill(void *h, uint32_t T, int wantLogits, cudaStream_t stream) {
     return dl::enginePrefill(*(Engine *)h, T, wantLogits, stream);
 }

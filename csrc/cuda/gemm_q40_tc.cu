@@ -735,6 +735,7 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
         const uint32_t nkq = n / 256;
         uint32_t sk = (uint32_t)numSms / nTilesM;
         if (sk > 8) sk = 8;
+        if (nkq < 32) sk = 1;             // K < 8192 (qkv, wo): the GEMM is short, splitting only adds the scratch round trip
         if (sk > nkq / 8) sk = nkq / 8;   // every split keeps >= 8 raw chunks (2048 of K): below that the scratch round trip costs more than it saves
         if (sk >= 2) {
             const size_t need = (size_t)sk * T * d * sizeof(float);

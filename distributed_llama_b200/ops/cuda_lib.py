@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
     L.dl_engine_num_sms.restype = u32
     L.dl_engine_forward.argtypes = [vp, i32, i32, i32, vp]
     L.dl_engine_forward.restype = i32
+    L.dl_engine_forward_part.argtypes = [vp, i32, u32, i32, vp, vp]
+    L.dl_engine_forward_part.restype = i32
     L.dl_engine_prefill.argtypes = [vp, u32, i32, vp]
     L.dl_engine_prefill.restype = i32
     L.dl_engine_capture_decode.argtypes = [vp]

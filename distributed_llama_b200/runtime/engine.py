@@ -201,6 +201,27 @@ class Engine:
         self.forward_batch(tokens, start_pos, logits_mode=2)
         return self._full_logits(self.logits[: len(tokens)])
 
+    # -- NCCL baseline (tensor parallel): same kernels, collectives through torch.distributed instead of in-kernel ----
+    def forward_nccl_baseline(self, token_count: int = 1) -> torch.Tensor:
+        """One forward over the tokens already staged in self.tokens/self.pos with per-layer NCCL all-reduces (the reference's
+        K2/K3 sync sites as library collectives). Used to quantify what the fused in-kernel all-reduce buys; capturable in a
+        torch CUDA graph. Returns the local logits slice."""
+        import torch.distributed as dist
+        nb = token_count
+        if not hasattr(self, "_ybuf"):
+            self._ybuf = torch.zeros(self.max_batch, self.w.header.dim, dtype=torch.float32, device=self.device)
+        y, sp, lib, h = self._ybuf, cl.stream_ptr(), self._lib, self._h
+        tp = self.comm is not None and self.comm.world_size > 1
+        cl.check(lib.dl_engine_forward_part(h, nb, 0, 0, y.data_ptr(), sp), "forward_part")
+        for l in range(self.w.header.n_layers):
+            for part in (1, 2):
+                cl.check(lib.dl_engine_forward_part(h, nb, l, part, y.data_ptr(), sp), "forward_part")
+                if tp:
+                    dist.all_reduce(y[:nb])
+                self.x[:nb].add_(y[:nb])
+        cl.check(lib.dl_engine_forward_part(h, nb, 0, 3, y.data_ptr(), sp), "forward_part")
+        return self.logits[0]
+
     # -- device-resident greedy decoding --
     def run_decode_step(self, use_graph: bool = True):
         """One greedy step on whatever (token, pos) currently sit in device memory; result lands in tokens[0]."""
