@@ -48,7 +48,8 @@ def main():
         eng3.enable_mega()
     eng3.prefill(prompt[:-1], 0, want_logits=False)
     toks_eager = eng3.decode_greedy(prompt[-1], len(prompt) - 1, 32, use_graph=False)
-    # tensor-core prefill under TP (fused GEMM + all-reduce) followed by a decode step
+    # tensor-core prefill under TP (fused GEMM + all-reduce); bf16 activations, so the tolerance matches the
+    # single-GPU tensor-core-prefill test (0.12), not the bit-exact decode path
     long_prompt = [(7 * i + 3) % 500 + 1 for i in range(45)]
     eng4 = Engine(load_device_weights(mf, comm.rank, comm.world_size, moe_mode=moe_mode), comm=comm)
     lg_pf = eng4.prefill(long_prompt, 0).clone()
@@ -76,7 +77,7 @@ def main():
         n_agree = sum(a == b for a, b in zip(toks_graph, ref_toks))
         print(f"moe_mode={eng.w.moe_mode} tp={comm.world_size} max|tp - tp1|={e1:.4g} max|tp - oracle|={e2:.4g} greedy agree {n_agree}/32 "
               f"graph==eager {toks_graph == toks_eager} ranks agree {same_across_ranks}")
-        ok = e3 < 0.05 and e1 < 0.05 and e2 < 0.08 and toks_graph == toks_eager and same_across_ranks and n_agree >= 8
+        ok = e3 < 0.12 and e1 < 0.05 and e2 < 0.08 and toks_graph == toks_eager and same_across_ranks and n_agree >= 8
         print("mega" if mega else "multi-kernel", "decode path")
         print("TP_CHECK", "PASS" if ok else "FAIL")
     dist.barrier()
