@@ -23,6 +23,7 @@ struct EngineConfig {   // mirrored by ctypes in distributed_llama_b200/ops/cuda
     float eps;
     uint32_t usePdl;
     uint32_t moeFirstExpert, moeNumLocal;   // experts held by this rank (expert parallelism); TP mode: 0, nExperts
+    uint32_t wType;          // matrix storage: 0 = q40 device layout, 1 = dense f32, 2 = dense f16 (gemv_dense.cu)
 };
 
 struct LayerPtrs {
@@ -108,6 +109,7 @@ static void fillAr(const Engine &e, ArArgs &ar, uint32_t parity) {
 }
 
 static int gemvSel(const Engine &e, int pro, int epi, int nb, const GemvArgs &a, int numSms, cudaStream_t stream, bool pdl) {
+    if (e.cfg.wType != 0) return gemvDense((int)e.cfg.wType, pro, epi, nb, a, numSms, stream, pdl);
     if (a.ar.nRanks > 1) {   // the in-kernel all-reduce lives in the TMA kernel only
         const int r = gemvQ40Tma(pro, epi, nb, a, numSms, stream, pdl);
         return r == 1 ? -30 : r;
@@ -115,10 +117,40 @@ static int gemvSel(const Engine &e, int pro, int epi, int nb, const GemvArgs &a,
     return e.useTma ? gemvQ40Auto(pro, epi, nb, a, numSms, stream, pdl) : gemvQ40(pro, epi, nb, a, numSms, stream, pdl);
 }
 
+// Mixture-of-experts feed-forward of one token: router -> k x (W1|W3 -> silu*up) -> k x W2; the weighted expert sum is
+// *added* to `out` (the residual stream, or a zeroed partial buffer on the NCCL path), all-reduced in the epilogue if asked.
+static int runMoe(Engine &e, const LayerPtrs &L, float *out, bool fusedAr, uint64_t *trace13, uint64_t *trace2, cudaStream_t stream,
+                  bool pdl) {
+    const EngineConfig &c = e.cfg;
+    if (c.wType != 0) return -34;   // expert-indexed kernels exist for q40 matrices only
+    RouterArgs ro{};
+    ro.x = e.g.x; ro.normW = L.norm1; ro.gate = L.moeGate; ro.eps = c.eps; ro.dim = c.dim; ro.nExperts = c.nExperts;
+    ro.k = c.nActiveExperts; ro.logits = e.g.routerLogits; ro.counter = e.g.routerCounter; ro.expertIdx = e.g.expertIdx;
+    ro.expertWeight = e.g.expertWeight;
+    DL_TRY(launchMoeRouter(ro, 1, stream, pdl));
+    const uint32_t perSlot = c.numSms / c.nActiveExperts > 0 ? c.numSms / c.nActiveExperts : 1;
+    GemvArgs a{};
+    a.qs = (const uint32_t *)L.w13Qs; a.scales = (const __half *)L.w13Sc; a.d = 2 * c.ffDim; a.n = c.dim;
+    a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm1; a.eps = c.eps; a.out = e.g.h; a.outStride = c.ffDim; a.trace = trace13;
+    a.moeCtasPerSlot = perSlot; a.kActive = c.nActiveExperts; a.expertIdx = e.g.expertIdx; a.outSlotStride = c.ffDim;
+    a.expertQsStride = (uint64_t)2 * c.ffDim * (c.dim / 8); a.expertScaleStride = (uint64_t)2 * c.ffDim * (c.dim / 32);
+    a.moeFirstExpert = c.moeFirstExpert; a.moeNumLocal = c.moeNumLocal;
+    { const int r = gemvQ40Tma(PRO_RMSNORM_, EPI_SWIGLU_, 1, a, c.numSms, stream, pdl); if (r != 0) return r == 1 ? -31 : r; }
+    a = GemvArgs{};
+    a.qs = (const uint32_t *)L.w2Qs; a.scales = (const __half *)L.w2Sc; a.d = c.dim; a.n = c.ffDim;
+    a.in = e.g.h; a.inStride = c.ffDim; a.inSlotStride = c.ffDim; a.out = out; a.outStride = c.dim; a.trace = trace2;
+    a.moeCtasPerSlot = perSlot; a.kActive = c.nActiveExperts; a.expertIdx = e.g.expertIdx; a.expertWeight = e.g.expertWeight;
+    a.expertQsStride = (uint64_t)c.dim * (c.ffDim / 8); a.expertScaleStride = (uint64_t)c.dim * (c.ffDim / 32);
+    a.moeFirstExpert = c.moeFirstExpert; a.moeNumLocal = c.moeNumLocal; a.moeScratch = e.g.moeScratch; a.moeCounters = e.g.moeCounters;
+    if (fusedAr) fillAr(e, a.ar, 1);
+    { const int r = gemvQ40Tma(PRO_PLAIN_, EPI_MOE_DOWN_, 1, a, c.numSms, stream, pdl); if (r != 0) return r == 1 ? -32 : r; }
+    return 0;
+}
+
 // One token through the persistent kernel (dense models, nb == 1). Returns 1 when the shape is not supported.
 static int engineDecodeMega(Engine &e, bool greedyAdvance, cudaStream_t stream) {
     const EngineConfig &c = e.cfg;
-    if (!e.megaLayers || c.nExperts > 0) return 1;
+    if (!e.megaLayers || c.nExperts > 0 || c.wType != 0) return 1;
     MegaArgs m{};
     m.layers = e.megaLayers; m.nLayers = c.nLayers; m.dim = c.dim; m.nHeads = c.nHeads; m.nKvHeads = c.nKvHeads; m.headDim = c.headDim;
     m.ffDim = c.ffDim; m.vocab = c.vocab; m.vocabFull = e.g.vocabFull; m.seqLen = c.seqLen; m.nSplits = c.nSplits; m.eps = c.eps;
@@ -186,28 +218,9 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
         if (c.nExperts > 0) {
             // 5-7. mixture of experts: router -> k x (W1|W3 -> silu*up) -> k x W2, weighted sum, residual (+ all-reduce)
             if (nb != 1) return -13;
-            RouterArgs ro{};
-            ro.x = e.g.x; ro.normW = L.norm1; ro.gate = L.moeGate; ro.eps = c.eps; ro.dim = c.dim; ro.nExperts = c.nExperts;
-            ro.k = c.nActiveExperts; ro.logits = e.g.routerLogits; ro.counter = e.g.routerCounter; ro.expertIdx = e.g.expertIdx;
-            ro.expertWeight = e.g.expertWeight;
             nextTrace();
-            DL_TRY(launchMoeRouter(ro, nb, stream, pdl));
-            const uint32_t perSlot = c.numSms / c.nActiveExperts > 0 ? c.numSms / c.nActiveExperts : 1;
-            a = GemvArgs{};
-            a.qs = (const uint32_t *)L.w13Qs; a.scales = (const __half *)L.w13Sc; a.d = 2 * c.ffDim; a.n = c.dim;
-            a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm1; a.eps = c.eps; a.out = e.g.h; a.outStride = c.ffDim; a.trace = nextTrace();
-            a.moeCtasPerSlot = perSlot; a.kActive = c.nActiveExperts; a.expertIdx = e.g.expertIdx; a.outSlotStride = c.ffDim;
-            a.expertQsStride = (uint64_t)2 * c.ffDim * (c.dim / 8); a.expertScaleStride = (uint64_t)2 * c.ffDim * (c.dim / 32);
-            a.moeFirstExpert = c.moeFirstExpert; a.moeNumLocal = c.moeNumLocal;
-            { const int r = gemvQ40Tma(PRO_RMSNORM_, EPI_SWIGLU_, 1, a, c.numSms, stream, pdl); if (r != 0) return r == 1 ? -31 : r; }
-            a = GemvArgs{};
-            a.qs = (const uint32_t *)L.w2Qs; a.scales = (const __half *)L.w2Sc; a.d = c.dim; a.n = c.ffDim;
-            a.in = e.g.h; a.inStride = c.ffDim; a.inSlotStride = c.ffDim; a.out = e.g.x; a.outStride = c.dim; a.trace = nextTrace();
-            a.moeCtasPerSlot = perSlot; a.kActive = c.nActiveExperts; a.expertIdx = e.g.expertIdx; a.expertWeight = e.g.expertWeight;
-            a.expertQsStride = (uint64_t)c.dim * (c.ffDim / 8); a.expertScaleStride = (uint64_t)c.dim * (c.ffDim / 32);
-            a.moeFirstExpert = c.moeFirstExpert; a.moeNumLocal = c.moeNumLocal; a.moeScratch = e.g.moeScratch; a.moeCounters = e.g.moeCounters;
-            if (e.comm.nRanks > 1) fillAr(e, a.ar, 1);
-            { const int r = gemvQ40Tma(PRO_PLAIN_, EPI_MOE_DOWN_, 1, a, c.numSms, stream, pdl); if (r != 0) return r == 1 ? -32 : r; }
+            uint64_t *t13 = nextTrace(), *t2 = nextTrace();
+            DL_TRY(runMoe(e, L, e.g.x, e.comm.nRanks > 1, t13, t2, stream, pdl));
             continue;
         }
         // 5. rmsnorm -> q80 -> W1|W3 -> silu*up
@@ -229,7 +242,7 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
         if (logitsMode == 1) {
             a.in = e.g.x + (size_t)(nb - 1) * c.dim;
             int r = 1;
-            if (greedyAdvance && e.fusedArgmax) {
+            if (greedyAdvance && e.fusedArgmax && c.wType == 0) {
                 // logits + greedy sampling + position advance in one launch
                 a.argVal = e.g.argVal; a.argIdx = e.g.argIdx; a.argCounter = e.g.argCounter;
                 a.tokenOut = e.g.tokens; a.posInOut = e.g.pos; a.history = e.g.history; a.historyCap = c.seqLen;
@@ -260,6 +273,7 @@ static int enginePrefill(Engine &e, uint32_t T, int wantLogits, cudaStream_t str
     const bool pdl = false;   // plain stream order between the heterogeneous kernels of this path
     const uint32_t qDim = c.nHeads * c.headDim, kvDim = c.nKvHeads * c.headDim, qkvDim = qDim + 2 * kvDim;
     if (T < 1 || T > g.maxPrefill || T > 256) return -11;
+    if (c.wType != 0 || c.nExperts > 0) return -35;   // tensor-core path: dense-model q40 matrices
     const bool tp = e.comm.nRanks > 1;
     ArArgs arP{};
     if (tp) {
@@ -381,29 +395,32 @@ DL_EXPORT int dl_engine_forward(void *h, int nb, int logitsMode, int greedyAdvan
     return dl::engineForward(*(Engine *)h, nb, logitsMode, greedyAdvance != 0, stream);
 }
 
-// NCCL-baseline building blocks (decode path, nb tokens): the same kernels, but the tensor-parallel partial products are
-// *stored* into `ybuf` instead of being all-reduced in the epilogue; the caller all-reduces ybuf with NCCL and adds it to x.
+// Library-collective building blocks (decode path, nb tokens): the same kernels, but the tensor-parallel partial products
+// are *stored* into `ybuf` instead of being all-reduced in the epilogue; the caller all-reduces ybuf with NCCL and adds it
+// to x. Used (a) as the NCCL baseline the fused kernels are measured against, (b) as the execution path when ranks do not
+// share an NVLink/IPC domain (multi-node) and (c) for dense f32/f16 weight files under tensor parallelism.
 //   part 0: embedding              part 1: QKV + attention + WO -> ybuf
-//   part 2: W1|W3 + W2 -> ybuf     part 3: logits (local vocabulary slice)
+//   part 2: feed-forward -> ybuf   part 3: logits of the last token (local vocabulary slice)   part 4: logits of all nb tokens
 DL_EXPORT int dl_engine_forward_part(void *h, int nb, uint32_t layer, int part, float *ybuf, cudaStream_t stream) {
     Engine &e = *(Engine *)h;
     const dl::EngineConfig &c = e.cfg;
     const uint32_t qDim = c.nHeads * c.headDim, kvDim = c.nKvHeads * c.headDim, qkvDim = qDim + 2 * kvDim;
+    if (nb < 1 || (uint32_t)nb > c.maxBatch || (nb & (nb - 1))) return -10;
     if (part == 0) return dl::launchEmbedding(e.g.embedding, e.g.tokens, e.g.x, c.dim, c.dim, e.g.vocabFull, nb, stream);
-    if (part == 3) {
+    if (part == 3 || part == 4) {
         dl::GemvArgs a{};
         a.qs = (const uint32_t *)e.g.wclsQs; a.scales = (const __half *)e.g.wclsSc; a.d = c.vocab; a.n = c.dim;
         a.normW = e.g.finalNorm; a.eps = c.eps; a.inStride = c.dim; a.outStride = c.vocab; a.out = e.g.logits;
-        a.in = e.g.x + (size_t)(nb - 1) * c.dim;
-        return dl::gemvQ40Auto(dl::PRO_RMSNORM_, dl::EPI_STORE_, 1, a, c.numSms, stream, false);
+        a.in = part == 3 ? e.g.x + (size_t)(nb - 1) * c.dim : e.g.x;
+        return dl::gemvSel(e, dl::PRO_RMSNORM_, dl::EPI_STORE_, part == 3 ? 1 : nb, a, c.numSms, stream, false);
     }
-    if (layer >= c.nLayers || c.nExperts > 0) return -1;
+    if (layer >= c.nLayers) return -1;
     const dl::LayerPtrs &L = e.layers[layer];
     dl::GemvArgs a{};
     if (part == 1) {
         a.qs = (const uint32_t *)L.qkvQs; a.scales = (const __half *)L.qkvSc; a.d = qkvDim; a.n = c.dim;
         a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm0; a.eps = c.eps; a.out = e.g.qkv; a.outStride = qkvDim;
-        DL_TRY(dl::gemvQ40Auto(dl::PRO_RMSNORM_, dl::EPI_STORE_, nb, a, c.numSms, stream, false));
+        DL_TRY(dl::gemvSel(e, dl::PRO_RMSNORM_, dl::EPI_STORE_, nb, a, c.numSms, stream, false));
         dl::RopeKvArgs r{};
         r.qkv = e.g.qkv; r.qkvStride = qkvDim; r.pos = e.g.pos; r.rope = e.g.rope; r.qNorm = L.qNorm; r.kNorm = L.kNorm;
         r.eps = c.eps; r.nHeads = c.nHeads; r.nKvHeads = c.nKvHeads; r.headDim = c.headDim; r.seqLen = c.seqLen;
@@ -417,16 +434,21 @@ DL_EXPORT int dl_engine_forward_part(void *h, int nb, uint32_t layer, int part, 
         a = dl::GemvArgs{};
         a.qs = (const uint32_t *)L.woQs; a.scales = (const __half *)L.woSc; a.d = c.dim; a.n = qDim;
         a.in = e.g.z; a.inStride = qDim; a.out = ybuf; a.outStride = c.dim;
-        return dl::gemvQ40Auto(dl::PRO_PLAIN_, dl::EPI_STORE_, nb, a, c.numSms, stream, false);
+        return dl::gemvSel(e, dl::PRO_PLAIN_, dl::EPI_STORE_, nb, a, c.numSms, stream, false);
+    }
+    if (part == 2 && c.nExperts > 0) {
+        if (nb != 1) return -13;
+        DL_CUDA_CHECK(cudaMemsetAsync(ybuf, 0, (size_t)c.dim * sizeof(float), stream));
+        return dl::runMoe(e, L, ybuf, false, nullptr, nullptr, stream, false);
     }
     if (part == 2) {
         a.qs = (const uint32_t *)L.w13Qs; a.scales = (const __half *)L.w13Sc; a.d = 2 * c.ffDim; a.n = c.dim;
         a.in = e.g.x; a.inStride = c.dim; a.normW = L.norm1; a.eps = c.eps; a.out = e.g.h; a.outStride = c.ffDim;
-        DL_TRY(dl::gemvQ40Auto(dl::PRO_RMSNORM_, dl::EPI_SWIGLU_, nb, a, c.numSms, stream, false));
+        DL_TRY(dl::gemvSel(e, dl::PRO_RMSNORM_, dl::EPI_SWIGLU_, nb, a, c.numSms, stream, false));
         a = dl::GemvArgs{};
         a.qs = (const uint32_t *)L.w2Qs; a.scales = (const __half *)L.w2Sc; a.d = c.dim; a.n = c.ffDim;
         a.in = e.g.h; a.inStride = c.ffDim; a.out = ybuf; a.outStride = c.dim;
-        return dl::gemvQ40Auto(dl::PRO_PLAIN_, dl::EPI_STORE_, nb, a, c.numSms, stream, false);
+        return dl::gemvSel(e, dl::PRO_PLAIN_, dl::EPI_STORE_, nb, a, c.numSms, stream, false);
     }
     return -2;
 }

@@ -54,6 +54,9 @@ inline int gemvQ40Auto(int pro, int epi, int nb, const GemvArgs &a, int numSms, 
     return r == 1 ? gemvQ40(pro, epi, nb, a, numSms, stream, pdl) : r;
 }
 
+// f32 / f16 weight files (gemv_dense.cu): wtype 1 = f32, 2 = f16; a.qs is the row-major [d][n] matrix
+int gemvDense(int wtype, int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl);
+
 struct RopeKvArgs {
     float *qkv;
     uint32_t qkvStride;

@@ -23,7 +23,7 @@ import torch
 from .. import host
 from ..formats.model_file import ModelFile
 from ..formats import quants
-from ..ops.q40 import DeviceQ40, repack_q40
+from ..ops.q40 import DeviceDense, DeviceQ40, repack_q40
 from .config import ROPE_FALCON
 
 
@@ -58,6 +58,7 @@ class DeviceWeights:
     first_expert: int = 0        # experts held by this rank (expert parallelism), all of them in TP mode
     n_local_experts: int = 0
     moe_mode: str = "tp"
+    weight_kind: int = 0         # 0 = q40 device layout, 1 = dense f32, 2 = dense f16
 
 
 def _interleave_perm(head_dim: int) -> np.ndarray:
@@ -92,13 +93,64 @@ class _Uploader:
         return torch.from_numpy(np.ascontiguousarray(x)).to(self.device)
 
 
+def _load_dense(mf: ModelFile, up: "_Uploader", rank, n_ranks, kv_rank, kv_ranks, nh, nkv, ff0, v0, neox, device) -> "DeviceWeights":
+    """f32 / f16 / q80 weight files: matrices stay dense on the device (f16 files as f16, everything else as f32 — q80 blocks
+    are dequantised exactly) and run through csrc/cuda/gemv_dense.cu with f32 activations. This is the reference's
+    F32_F32_F32 matmul path (`--buffer-float-type f32`, src/nn/nn-cpu-ops.cpp:1138-1160); same partition rules."""
+    h = mf.header
+    H = host()
+    hd, dim = h.head_dim, h.dim
+    dt = torch.float16 if h.weight_type == quants.F_16 else torch.float32
+
+    def sliced(name, layer, r, n):
+        x = mf.slice_f32(mf.entry(name, layer, 0), r, n)
+        up.bytes += x.nbytes
+        return torch.from_numpy(np.ascontiguousarray(x))
+
+    def heads_interleaved(x, n_heads):
+        if not neox:
+            return x
+        perm = torch.from_numpy(_interleave_perm(hd))
+        return x.reshape(n_heads, hd, x.shape[1])[:, perm, :].reshape(n_heads * hd, x.shape[1])
+
+    def dev(x, d, n):
+        return DeviceDense(x.to(dt).contiguous().to(device), d, n)
+
+    W = DeviceWeights(header=h, rank=rank, n_ranks=n_ranks, n_heads=nh, n_kv_heads=nkv, ff_dim=ff0, vocab=v0,
+                      embedding=up.f32(mf.entry("embedding")), final_norm=up.f32(mf.entry("final_norm")),
+                      wcls=dev(sliced("final_matmul_logits", 0, rank, n_ranks), v0, dim),
+                      rope=torch.from_numpy(np.asarray(H.build_rope_table(h, h.seq_len))).to(device))
+    perm_dev = torch.from_numpy(_interleave_perm(hd)).to(device) if neox else None
+    for l in range(h.n_layers):
+        q = heads_interleaved(sliced("block_matmul_q", l, rank, n_ranks), nh)
+        k = heads_interleaved(sliced("block_matmul_k", l, kv_rank, kv_ranks), nkv)
+        v = sliced("block_matmul_v", l, kv_rank, kv_ranks)
+        w1, w3 = sliced("block_matmul_w1", l, rank, n_ranks), sliced("block_matmul_w3", l, rank, n_ranks)
+        L = LayerWeights(qkv=dev(torch.cat([q, k, v], 0), (nh + 2 * nkv) * hd, dim),
+                         wo=dev(sliced("block_matmul_wo", l, rank, n_ranks), dim, nh * hd),
+                         w13=dev(torch.stack([w1, w3], 1).reshape(2 * ff0, dim), 2 * ff0, dim),
+                         w2=dev(sliced("block_matmul_w2", l, rank, n_ranks), dim, ff0),
+                         norm0=up.f32(mf.entry("block_norm_0", l)), norm1=up.f32(mf.entry("block_norm_1", l)))
+        if h.qk_norm:
+            qn, kn = up.f32(mf.entry("block_norm_q", l)), up.f32(mf.entry("block_norm_k", l))
+            L.q_norm = qn[perm_dev].contiguous() if neox else qn
+            L.k_norm = kn[perm_dev].contiguous() if neox else kn
+        W.layers.append(L)
+    if torch.device(device).type == "cuda":
+        torch.cuda.synchronize(device)
+    W.bytes_uploaded = up.bytes
+    W.weight_kind = 1 if dt == torch.float32 else 2
+    return W
+
+
 def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="cuda", moe_mode: str = "auto") -> DeviceWeights:
     """moe_mode (Qwen3-MoE only): "tp" slices every expert over the ranks like the reference (src/llm.cpp:454-486);
     "ep" gives each rank nExperts/nRanks whole experts (expert parallelism: the expert FFN streams full-width matrices and the
     combine is the same in-kernel all-reduce); "auto" picks ep when the TP slice would be narrower than 128 columns."""
     h = mf.header
-    if h.weight_type != quants.F_Q40:
-        raise NotImplementedError("the CUDA engine currently runs q40 weight files (as the reference's GPU/CPU fast path)")
+    dense = h.weight_type != quants.F_Q40
+    if dense and h.n_experts > 0:
+        raise NotImplementedError("mixture-of-experts models need q40 weights (the expert-routed kernels are q40 only)")
     H = host()
     if moe_mode == "auto":
         moe_mode = "ep" if (h.n_experts > 0 and n_ranks > 1 and (h.ff_dim // n_ranks) % 128 != 0 and h.n_experts % n_ranks == 0) else "tp"
@@ -124,6 +176,8 @@ def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="
     neox = h.rope_type == ROPE_FALCON
     up = _Uploader(mf, device)
     dim = h.dim
+    if dense:
+        return _load_dense(mf, up, rank, n_ranks, kv_rank, kv_ranks, nh, nkv, ff0, v0, neox, device)
 
     def row_sliced(name, layer, expert, dst: DeviceQ40, rows_local, dst_stride=1, dst_off=0, head_dim=0, slice_rank=None):
         e = mf.entry(name, layer, expert)

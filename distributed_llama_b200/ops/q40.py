@@ -31,6 +31,42 @@ class DeviceQ40:
         return out
 
 
+@dataclass
+class DeviceDense:
+    """Row-major f32 / f16 matrix [lead*d][n] for `.m` files that are not q40 (csrc/cuda/gemv_dense.cu). Exposes the same
+    `qs` / `scales` attributes as DeviceQ40 so the engine's pointer tables do not care which kind they carry."""
+    data: torch.Tensor
+    d: int
+    n: int
+
+    @property
+    def qs(self) -> torch.Tensor:
+        return self.data
+
+    @property
+    def scales(self):
+        return None
+
+    @property
+    def wtype(self) -> int:
+        return 1 if self.data.dtype == torch.float32 else 2
+
+    def to_f32(self) -> torch.Tensor:
+        return self.data.float()
+
+
+def gemv_dense(w: DeviceDense, x: torch.Tensor, *, pro: int, epi: int, out: torch.Tensor, norm_w: Optional[torch.Tensor] = None,
+               eps: float = 1e-5, num_sms: int = 0, pdl: bool = False) -> torch.Tensor:
+    """Dense-weight counterpart of gemv_q40 (f32 activations, no q80 round trip)."""
+    nb = x.shape[0]
+    if num_sms == 0:
+        num_sms = torch.cuda.get_device_properties(x.device).multi_processor_count
+    cl.check(cl.lib().dl_gemv_dense(w.wtype, pro, epi, nb, w.data.data_ptr(), w.d, w.n, x.data_ptr(), x.stride(0),
+                                    norm_w.data_ptr() if norm_w is not None else None, eps, out.data_ptr(), out.stride(0),
+                                    num_sms, cl.stream_ptr(), 1 if pdl else 0), "gemv_dense")
+    return out
+
+
 def repack_q40(raw: torch.Tensor, rows: int, n_cols: int, dst: DeviceQ40, *, src_row_pitch: Optional[int] = None,
                src_col_byte_offset: int = 0, dst_row_stride: int = 1, dst_row_offset: int = 0, head_dim: int = 0) -> None:
     """raw: uint8 CUDA tensor holding `rows` source rows of 18-byte blocks (pitch defaults to n_cols/32*18)."""

@@ -58,6 +58,11 @@ class Communicator:
         self.arena_ptrs: List[int] = []
         self.layout: ArenaLayout | None = None
         self._local = None
+        # Peer-memory (CUDA IPC over NVLink) collectives need every rank on one host; otherwise the engine falls back to NCCL.
+        import socket
+        hosts = [None] * self.world_size
+        dist.all_gather_object(hosts, socket.gethostname())
+        self.single_node = len(set(hosts)) == 1
 
     @property
     def is_root(self) -> bool:

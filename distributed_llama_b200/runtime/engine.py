@@ -24,7 +24,7 @@ def _p(t: Optional[torch.Tensor]):
 
 class Engine:
     def __init__(self, weights: DeviceWeights, max_batch: int = 8, n_splits: int = 0, use_pdl: bool = True,
-                 seq_len: Optional[int] = None, comm=None, max_prefill: int = 192):
+                 seq_len: Optional[int] = None, comm=None, max_prefill: int = 192, collectives: str = "auto"):
         self.w = w = weights
         h = w.header
         dev = w.embedding.device
@@ -32,6 +32,15 @@ class Engine:
         self.seq_len = seq_len or h.seq_len
         if h.n_experts > 0:
             max_batch = 1          # the MoE kernels route one token per launch
+        self.dense = getattr(w, "weight_kind", 0) != 0
+        if self.dense:
+            # f32 activations of all tokens of a launch are staged in shared memory (gemv_dense.cu)
+            widest = max(h.dim, w.ff_dim, w.n_heads * h.head_dim)
+            cap = (200 * 1024) // (4 * widest)
+            if cap < 1:
+                raise ValueError("matrix rows too wide for the dense-weight kernels on one GPU; use more ranks")
+            while max_batch > cap:
+                max_batch //= 2
         self.max_batch = max_batch
         props = torch.cuda.get_device_properties(dev)
         self.num_sms = props.multi_processor_count
@@ -79,7 +88,8 @@ class Engine:
                               ffDim=w.ff_dim, vocab=w.vocab, seqLen=self.seq_len, nExperts=h.n_experts,
                               nActiveExperts=h.n_active_experts, maxBatch=max_batch, nSplits=n_splits, rank=w.rank,
                               nRanks=w.n_ranks, numSms=self.num_sms, eps=h.norm_epsilon, usePdl=1 if use_pdl else 0,
-                              moeFirstExpert=w.first_expert, moeNumLocal=w.n_local_experts)
+                              moeFirstExpert=w.first_expert, moeNumLocal=w.n_local_experts,
+                              wType=getattr(w, "weight_kind", 0))
         self._lib = cl.lib()
         self._h = self._lib.dl_engine_create(C.byref(cfg))
         for l, L in enumerate(w.layers):
@@ -101,14 +111,23 @@ class Engine:
                            argVal=_p(self.arg_val), argIdx=_p(self.arg_idx), argCounter=_p(self.arg_counter))
         cl.check(self._lib.dl_engine_set_globals(self._h, C.byref(gp)), "engine_set_globals")
         self.comm = comm
-        if comm is not None and comm.world_size > 1:
+        tp = comm is not None and comm.world_size > 1
+        # Collectives: "fused" = inside the kernels over NVLink peer memory (ranks of one node, q40 weights);
+        # "nccl" = library all-reduce between kernel groups (ranks on several nodes, dense weight files, DL_COLLECTIVES=nccl).
+        self.collectives = "fused"
+        if tp and (collectives == "nccl" or os.environ.get("DL_COLLECTIVES") == "nccl" or self.dense
+                   or not getattr(comm, "single_node", True)):
+            self.collectives = "nccl"
+        if tp and self.collectives == "fused":
             from ..parallel.comm import arena_layout
             comm.alloc_arena(arena_layout(comm.world_size, max_batch, h.dim, h.vocab_size, self.max_prefill))
             cp = comm.comm_ptrs(max_batch * h.dim)
             cl.check(self._lib.dl_engine_set_comm(self._h, C.byref(cp)), "engine_set_comm")
-        self.use_tc_prefill = True
+        self._parts = tp and self.collectives == "nccl"
+        self._ybuf = torch.zeros(max_batch, h.dim, **f32)
+        self.use_tc_prefill = not self.dense and not self._parts
         self.mega = False
-        if h.n_experts == 0 and os.environ.get("DL_NO_MEGA") is None:
+        if h.n_experts == 0 and not self.dense and not self._parts and os.environ.get("DL_NO_MEGA") is None:
             self.enable_mega(True)     # persistent decode kernel by default; the engine falls back per call if a shape is unsupported
         self.tc_min_tokens = 9          # shorter chunks stay on the GEMV path
         self._graph_ready = False
@@ -155,7 +174,13 @@ class Engine:
         if start_pos + n > self.seq_len:
             raise ValueError("position beyond the context length")
         self._set_inputs(tokens, start_pos)
-        cl.check(self._lib.dl_engine_forward(self._h, n, logits_mode, 1 if greedy_advance else 0, cl.stream_ptr()), "engine_forward")
+        self._forward(n, logits_mode, greedy_advance)
+
+    def _forward(self, n: int, logits_mode: int, greedy_advance: bool = False):
+        if self._parts:
+            self._forward_parts(n, logits_mode, greedy_advance)
+        else:
+            cl.check(self._lib.dl_engine_forward(self._h, n, logits_mode, 1 if greedy_advance else 0, cl.stream_ptr()), "engine_forward")
 
     def prefill(self, tokens: Sequence[int], start_pos: int = 0, want_logits: bool = True) -> Optional[torch.Tensor]:
         """Feeds a prompt; returns the logits row of its last token (device tensor). Single GPU: chunks of up to 256 tokens
@@ -201,15 +226,12 @@ class Engine:
         self.forward_batch(tokens, start_pos, logits_mode=2)
         return self._full_logits(self.logits[: len(tokens)])
 
-    # -- NCCL baseline (tensor parallel): same kernels, collectives through torch.distributed instead of in-kernel ----
-    def forward_nccl_baseline(self, token_count: int = 1) -> torch.Tensor:
-        """One forward over the tokens already staged in self.tokens/self.pos with per-layer NCCL all-reduces (the reference's
-        K2/K3 sync sites as library collectives). Used to quantify what the fused in-kernel all-reduce buys; capturable in a
-        torch CUDA graph. Returns the local logits slice."""
+    # -- library-collective path (tensor parallel): same kernels, all-reduce through torch.distributed between kernel groups --
+    def _forward_parts(self, nb: int, logits_mode: int = 1, greedy_advance: bool = False) -> None:
+        """One forward over the tokens staged in self.tokens/self.pos with per-layer NCCL all-reduces (the reference's K2/K3
+        sync sites as library collectives, src/llm.cpp:397-403,548-554). Runs when the ranks do not share a peer-memory
+        domain, for dense weight files, and as the baseline the fused kernels are measured against. Graph capturable."""
         import torch.distributed as dist
-        nb = token_count
-        if not hasattr(self, "_ybuf"):
-            self._ybuf = torch.zeros(self.max_batch, self.w.header.dim, dtype=torch.float32, device=self.device)
         y, sp, lib, h = self._ybuf, cl.stream_ptr(), self._lib, self._h
         tp = self.comm is not None and self.comm.world_size > 1
         cl.check(lib.dl_engine_forward_part(h, nb, 0, 0, y.data_ptr(), sp), "forward_part")
@@ -219,12 +241,25 @@ class Engine:
                 if tp:
                     dist.all_reduce(y[:nb])
                 self.x[:nb].add_(y[:nb])
-        cl.check(lib.dl_engine_forward_part(h, nb, 0, 3, y.data_ptr(), sp), "forward_part")
+        if logits_mode:
+            cl.check(lib.dl_engine_forward_part(h, nb, 0, 3 if logits_mode == 1 else 4, y.data_ptr(), sp), "forward_part")
+        if greedy_advance:
+            tok = self._full_logits(self.logits[0]).argmax().to(torch.int32).reshape(1)
+            self.tokens[:1].copy_(tok)
+            self.pos[:1].add_(1)
+            self.history.index_copy_(0, self.pos[:1].long().clamp_(max=self.history.numel() - 1), tok)
+
+    def forward_nccl_baseline(self, token_count: int = 1) -> torch.Tensor:
+        """Library-collective forward of the staged tokens; returns the local logits slice (tools/bench_nccl_baseline.py)."""
+        self._forward_parts(token_count, 1, False)
         return self.logits[0]
 
     # -- device-resident greedy decoding --
     def run_decode_step(self, use_graph: bool = True):
         """One greedy step on whatever (token, pos) currently sit in device memory; result lands in tokens[0]."""
+        if self._parts:
+            self._forward_parts(1, 1, True)
+            return
         if use_graph:
             if not self._graph_ready:
                 saved = (self.tokens.clone(), self.pos.clone())
@@ -240,6 +275,8 @@ class Engine:
     def launches_per_decode_step(self) -> int:
         if self.mega:
             return 1                # one persistent kernel per token (plus a 4-byte memset node)
+        if self._parts:
+            return self.w.header.n_layers * 7 + 2
         if self.w.header.n_experts > 0:
             return self.w.header.n_layers * 6 + 2
         return self.w.header.n_layers * 5 + 2   # embedding + 5 fused kernels per layer + logits/arg-max
@@ -254,7 +291,10 @@ class Engine:
         if start_pos + n_steps > self.seq_len:
             raise ValueError("decode would run past the context length")
         self._set_inputs([first_token], start_pos)
-        if use_graph:
+        if self._parts:
+            for _ in range(n_steps):
+                self._forward_parts(1, 1, True)
+        elif use_graph:
             if not self._graph_ready:
                 # warm-up run configures kernel attributes outside of capture
                 cl.check(self._lib.dl_engine_forward(self._h, 1, 1, 0, cl.stream_ptr()), "engine_forward")

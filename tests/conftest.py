@@ -39,4 +39,11 @@ def tmp_models(tmp_path_factory):
         write_synthetic_model(m, cfg, seed=7)
         write_synthetic_tokenizer(t, cfg.vocab_size, style="chatml" if "qwen" in name else "llama3")
         out[name] = (m, t)
+    # non-q40 weight files (dense f32 / f16 kernels; q80 blocks are dequantised at load)
+    from distributed_llama_b200.formats import quants
+    for name, base, wt in (("tiny-llama31-f32", "tiny-llama31", quants.F_32), ("tiny-qwen3-f16", "tiny-qwen3", quants.F_16),
+                           ("tiny-llama-q80", "tiny-llama", quants.F_Q80)):
+        m = str(root / f"{name}.m")
+        write_synthetic_model(m, get_config(base), weights_float_type=wt, seed=7)
+        out[name] = (m, out[base][1])
     return out

@@ -101,3 +101,32 @@ def test_persistent_decode_kernel(tmp_models, name):
         toks = e.decode_greedy(prompt[-1], len(prompt) - 1, 40, use_graph=use_graph)
         agree = sum(a == b for a, b in zip(toks, ref_toks))
         assert agree >= 36, (toks, ref_toks)
+
+
+@pytest.mark.parametrize("name,tol", [("tiny-llama31-f32", 2e-2), ("tiny-qwen3-f16", 2e-2), ("tiny-llama-q80", 2e-2)])
+def test_dense_weight_files(tmp_models, name, tol):
+    """f32 / f16 / q80 weight files run on the dense GEMV kernels with f32 activations (reference: F32_F32_F32 matmul with
+    --buffer-float-type f32); compared with the oracle without activation quantisation (tolerance = the bf16 KV cache; the oracle keeps f32 KV)."""
+    from distributed_llama_b200.formats import ModelFile
+    from distributed_llama_b200.models.loader import load_device_weights
+    from distributed_llama_b200.models.reference import OracleModel
+    from distributed_llama_b200.runtime import Engine
+    mf = ModelFile(tmp_models[name][0])
+    eng = Engine(load_device_weights(mf))
+    assert eng.dense and not eng.mega
+    oracle = OracleModel(mf, act_quant="none", device="cuda")
+    toks = [3, 17, 250, 9, 44, 101, 7, 300, 12, 5, 77]
+    ref = oracle.forward(toks, 0)
+    lg = eng.prefill(toks[:8], 0).clone()                  # one 8-token batch
+    assert (lg - ref[7]).abs().max().item() < tol
+    for i in range(8, len(toks)):                          # then token by token
+        lg = eng.step(toks[i], i)
+        assert (lg - ref[i]).abs().max().item() < tol, i
+    # device-resident greedy loop (logits kernel + arg-max/advance kernel, graph replay) follows the oracle's arg-max
+    out = eng.decode_greedy(toks[-1], len(toks) - 1, 6)
+    tok, pos, want = toks[-1], len(toks) - 1, []
+    for _ in range(3):
+        tok = int(oracle.forward([tok], pos)[0].argmax())
+        want.append(tok)
+        pos += 1
+    assert out[:3] == want

@@ -101,3 +101,29 @@ def test_gemv_residual_and_swiglu(nb, impl):
     full = y @ wt.T
     ref = torch.nn.functional.silu(full[:, 0::2]) * full[:, 1::2]
     torch.testing.assert_close(hbuf, ref, rtol=3e-3, atol=3e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("nb", [1, 4])
+def test_gemv_dense_f32_f16_weights(dtype, nb):
+    """Dense-weight GEMV (f32 / f16 `.m` files): rmsnorm prologue and store / residual / SwiGLU epilogues vs PyTorch f32."""
+    from distributed_llama_b200.ops import DeviceDense, gemv_dense, PRO_RMSNORM, PRO_PLAIN, EPI_STORE, EPI_RESIDUAL, EPI_SWIGLU
+    torch.manual_seed(3)
+    d, n = 640, 1032 if dtype == torch.float32 else 1024          # n not a multiple of the unrolled chunk stride
+    w = (torch.randn(d, n, device="cuda") / n ** 0.5).to(dtype)
+    W = DeviceDense(w, d, n)
+    x = torch.randn(nb, n, device="cuda")
+    nw = torch.rand(n, device="cuda") + 0.5
+    wf = w.float()
+    xn = nw * x * torch.rsqrt((x * x).mean(-1, keepdim=True) + 1e-5)
+    out = torch.zeros(nb, d, device="cuda")
+    gemv_dense(W, x, pro=PRO_RMSNORM, epi=EPI_STORE, out=out, norm_w=nw, eps=1e-5)
+    torch.testing.assert_close(out, xn @ wf.T, rtol=1e-4, atol=1e-4)
+    res = torch.randn(nb, d, device="cuda")
+    out = res.clone()
+    gemv_dense(W, x, pro=PRO_PLAIN, epi=EPI_RESIDUAL, out=out)
+    torch.testing.assert_close(out, res + x @ wf.T, rtol=1e-4, atol=1e-4)
+    out = torch.zeros(nb, d // 2, device="cuda")
+    gemv_dense(W, x, pro=PRO_RMSNORM, epi=EPI_SWIGLU, out=out, norm_w=nw, eps=1e-5)
+    y = xn @ wf.T
+    torch.testing.assert_close(out, torch.nn.functional.silu(y[:, 0::2]) * y[:, 1::2], rtol=1e-4, atol=1e-4)

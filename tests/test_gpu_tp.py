@@ -40,6 +40,20 @@ def test_kv_head_replication_more_ranks_than_kv_heads():
     assert "TP_CHECK PASS" in r.stdout, r.stdout[-3000:]
 
 
+@pytest.mark.parametrize("model,moe_mode,wtype", [("tiny-llama31", "auto", "q40"), ("tiny-qwen3-moe", "tp", "q40"),
+                                                 ("tiny-llama31", "auto", "f32")])
+def test_library_collectives_path(model, moe_mode, wtype):
+    """NCCL all-reduce between kernel groups: the path taken across nodes (no shared peer-memory domain) and by dense
+    f32/f16 weight files; must agree with TP=1 and the oracle like the fused path does."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29655", os.path.join(ROOT, "tools", "tp_check.py"), model, moe_mode, wtype]
+    env = dict(os.environ, DL_COLLECTIVES="nccl")
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
+    assert "TP_CHECK PASS" in r.stdout and "collectives=nccl" in r.stdout, r.stdout[-3000:]
+
+
 def test_dllama_cli_spawns_ranks():
     """`dllama inference --gpus 2` (root + one worker process) prints the same continuation as the single-GPU run."""
     if torch.cuda.device_count() < 2:

@@ -18,13 +18,16 @@ from distributed_llama_b200.runtime import Engine
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "tiny-llama31"
     moe_mode = sys.argv[2] if len(sys.argv) > 2 else "auto"
+    wtype = sys.argv[3] if len(sys.argv) > 3 else "q40"        # q40 | f32 | f16 | q80 weight file
+    # env DL_COLLECTIVES=nccl: library all-reduce between kernel groups instead of the fused in-kernel one (multi-node path)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     comm = Communicator()
-    path = f"/tmp/tp_check_{name}.m"
+    from distributed_llama_b200.formats import quants
+    path = f"/tmp/tp_check_{name}_{wtype}.m"
     if comm.rank == 0:
-        write_synthetic_model(path, get_config(name), seed=11)
+        write_synthetic_model(path, get_config(name), weights_float_type=quants.parse_float_type(wtype), seed=11)
     dist.barrier()
     mf = ModelFile(path)
     mega = os.environ.get("DL_MEGA") == "1"
@@ -66,7 +69,7 @@ def main():
         single2 = Engine(load_device_weights(mf, 0, 1))
         single2.prefill(prompt[:-1], 0, want_logits=False)
         ref_toks = single2.decode_greedy(prompt[-1], len(prompt) - 1, 32)
-        oracle = OracleModel(mf, act_quant="q80", device="cuda")
+        oracle = OracleModel(mf, act_quant="q80" if wtype == "q40" else "none", device="cuda")
         olg = oracle.forward(prompt, 0)
         single3 = Engine(load_device_weights(mf, 0, 1))
         ref_pf = single3.prefill(long_prompt, 0).clone()
@@ -75,7 +78,7 @@ def main():
         e1 = (lg - ref_lg).abs().max().item()
         e2 = (lg - olg).abs().max().item()
         n_agree = sum(a == b for a, b in zip(toks_graph, ref_toks))
-        print(f"moe_mode={eng.w.moe_mode} tp={comm.world_size} max|tp - tp1|={e1:.4g} max|tp - oracle|={e2:.4g} greedy agree {n_agree}/32 "
+        print(f"moe_mode={eng.w.moe_mode} weights={wtype} collectives={eng.collectives} tp={comm.world_size} max|tp - tp1|={e1:.4g} max|tp - oracle|={e2:.4g} greedy agree {n_agree}/32 "
               f"graph==eager {toks_graph == toks_eager} ranks agree {same_across_ranks}")
         ok = e3 < 0.12 and e1 < 0.05 and e2 < 0.08 and toks_graph == toks_eager and same_across_ranks and n_agree >= 8
         print("mega" if mega else "multi-kernel", "decode path")
