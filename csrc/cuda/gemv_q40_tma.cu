@@ -81,9 +81,10 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
                 scBase += (uint64_t)e * a.expertScaleStride * 2;
             }
             const uint64_t policy = policyEvictFirst();
+            uint32_t st = 0, par = 0;
+            bool wrapped = false;
             for (uint32_t f = 0; f < nFills; f++) {
-                const uint32_t st = f % geo.nStages;
-                if (f >= geo.nStages) mbarWait(&emptyBar[st], ((f / geo.nStages) - 1) & 1);
+                if (wrapped) mbarWait(&emptyBar[st], par ^ 1u);
                 const uint32_t r0 = f * SR;
                 const uint32_t rows = min(SR, tileRows - r0);
                 const uint32_t bq = rows * rowQsBytes, bs = rows * rowScBytes;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
                 mbarExpectTx(&fullBar[st], bq + bs);
                 tmaBulkLoad(dst, qsBase + (uint64_t)(rowBase + r0) * rowQsBytes, bq, &fullBar[st], policy);
                 tmaBulkLoad(dst + (size_t)SR * rowQsBytes, scBase + (uint64_t)(rowBase + r0) * rowScBytes, bs, &fullBar[st], policy);
+                if (++st == geo.nStages) { st = 0; par ^= 1u; wrapped = true; }
             }
         }
         return;
@@ -164,8 +166,13 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
     traceStamp(a.trace, 2);
 
     // ---- main loop over ring stages ----
+    // stage index / parity / step rotation are carried incrementally: no integer division inside the fill loop
+    const uint32_t stepsPerFullStage = (SR / kRowsPerStep) * nseg;
+    const uint32_t rotInc = stepsPerFullStage % kConsumerWarps;
+    const uint32_t gInc = kConsumerWarps / nseg, segInc = kConsumerWarps - gInc * nseg;
+    const uint32_t recipNseg = 65536u / nseg + 1u;   // (s * recip) >> 16 == s / nseg for s < 16, nseg <= 16
+    uint32_t st = 0, par = 0, rot = 0;
     for (uint32_t f = 0; active && f < nFills; f++) {
-        const uint32_t st = f % geo.nStages;
         const uint32_t r0 = f * SR;
         const uint32_t rows = min(SR, tileRows - r0);
         const uint32_t nGroups = (rows + kRowsPerStep - 1) / kRowsPerStep;
@@ -174,13 +181,12 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
         const uint4 *sq = reinterpret_cast<const uint4 *>(stage);
         const uint16_t *ss = reinterpret_cast<const uint16_t *>(stage + (size_t)SR * rowQsBytes);
         // steps are dealt round-robin over the 16 warps *across* fills (a stage may hold fewer than 16 steps)
-        const uint32_t stepsPerFullStage = (SR / kRowsPerStep) * nseg;
-        const uint32_t firstStep = (warp + kConsumerWarps - (f * stepsPerFullStage) % kConsumerWarps) % kConsumerWarps;
+        const uint32_t firstStep = ((uint32_t)warp - rot) & (kConsumerWarps - 1);
+        rot = (rot + rotInc) & (kConsumerWarps - 1);
         // every warp waits (even one without steps in this fill): it keeps all warps within one ring revolution, so no
         // warp can arrive twice on the same empty-barrier phase
-        mbarWait(&fullBar[st], (f / geo.nStages) & 1);
-        uint32_t g = firstStep / nseg, seg = firstStep - g * nseg;            // one division per fill, then incremental
-        const uint32_t gInc = kConsumerWarps / nseg, segInc = kConsumerWarps - gInc * nseg;
+        mbarWait(&fullBar[st], par);
+        uint32_t g = (firstStep * recipNseg) >> 16, seg = firstStep - g * nseg;
         for (uint32_t s = firstStep; s < nSteps; s += kConsumerWarps) {
             const uint32_t blk = seg * 32 + lane;
             const uint32_t rl = g * kRowsPerStep;                  // first row of the group inside the stage
@@ -241,6 +247,7 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
         }
         __syncwarp();
         if (lane == 0) mbarArrive(&emptyBar[st]);
+        if (++st == geo.nStages) { st = 0; par ^= 1u; }
     }
     consumerBarrier();
 

@@ -126,6 +126,13 @@ struct MegaLayer {
     __nv_bfloat16 *kCache, *vCache;
 };
 
+struct MegaPhase {   // host-computed geometry of one GEMV phase (QKV, WO, W1|W3, W2, logits)
+    uint32_t d, n, nblk, nseg;
+    uint32_t stageRows;            // rows per ring fill (multiple of 4)
+    uint32_t pairsQ, pairsRem;     // row pairs per CTA: CTA b owns pairsQ + (b < pairsRem) pairs starting at b*pairsQ + min(b, pairsRem)
+    uint32_t recipNseg, gInc, segInc, rotInc;   // step -> (row group, segment) bookkeeping without divisions
+};
+
 struct MegaArgs {
     const MegaLayer *layers;     // [nLayers] in global memory
     uint32_t nLayers, dim, nHeads, nKvHeads, headDim, ffDim, vocab, vocabFull, seqLen, nSplits;
@@ -141,6 +148,7 @@ struct MegaArgs {
     unsigned int *argCounter;
     unsigned int *gridCounter;   // zeroed by a memset node before every launch
     uint32_t stageBytes, nStages, planeBlocks, partialFloats;   // shared-memory geometry (host computed)
+    MegaPhase ph[5];
     uint32_t rowOffsetGlobal;
     uint32_t greedyAdvance;      // 1: publish the arg-max token and advance the position on the device
     uint64_t *trace;

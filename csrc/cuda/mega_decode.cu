@@ -15,9 +15,9 @@
 
 namespace dl {
 
-enum { MP_QKV = 0, MP_WO = 2, MP_W13 = 3, MP_W2 = 4, MP_LOGITS = 5 };
+enum { MP_QKV = 0, MP_WO = 1, MP_W13 = 2, MP_W2 = 3, MP_LOGITS = 4 };   // index into MegaArgs::ph
 
-__device__ __forceinline__ uint32_t megaStageRows(uint32_t n, uint32_t stageBytes) {
+static uint32_t megaStageRows(uint32_t n, uint32_t stageBytes) {
     const uint32_t rowBytes = (n / 32) * 18;
     uint32_t sr = stageBytes / rowBytes;
     sr = sr / 4 * 4;
@@ -46,20 +46,36 @@ __device__ __forceinline__ void gridBarrier(unsigned int *ctr, unsigned int &tar
 
 __device__ __forceinline__ float4 ldcg4(const float4 *p) { return __ldcg(p); }
 
-// One GEMV phase on the consumer warps. `fillIdx` is the running fill counter shared (by construction) with the producer.
+// Ring position shared (by construction) by the producer and the consumers: stage index + mbarrier phase parity, advanced
+// once per fill. Kept incrementally — the hot loop contains no integer division (every `%`/`/` by a runtime value costs a
+// ~20-instruction I2F/MUFU.RCP/F2I sequence per warp per fill, which used to dominate the per-fill overhead).
+struct RingPos {
+    uint32_t st, par;
+    __device__ __forceinline__ void advance(uint32_t nStages) {
+        if (++st == nStages) { st = 0; par ^= 1u; }
+    }
+};
+
+// This CTA's pair-aligned row tile of a phase: the first `pairsRem` CTAs own one pair more (host-computed quotient/remainder).
+__device__ __forceinline__ void megaTile(const MegaPhase &P, uint32_t &pairBegin, uint32_t &tileRows) {
+    const uint32_t b = blockIdx.x;
+    pairBegin = b * P.pairsQ + min(b, P.pairsRem);
+    tileRows = 2 * (P.pairsQ + (b < P.pairsRem ? 1u : 0u));
+}
+
+// One GEMV phase on the consumer warps.
 template <int PRO, int EPI>
-__device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, uint32_t d, uint32_t n, const float *in, const float *normW, float *out,
-                         uint32_t arParity, uint32_t &fillIdx, int tid, uint32_t &slot) {
+__device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase &P, const float *in, const float *normW, float *out,
+                         uint32_t arParity, RingPos &ring, int tid, uint32_t &slot) {
     auto stamp = [&]() { if (m.trace && blockIdx.x == 0 && tid == 0) m.trace[slot] = globalTimerNs(); slot++; };
     const int lane = tid & 31, warp = tid >> 5;
-    const uint32_t nblk = n / 32, nseg = (nblk + 31) / 32;
+    const uint32_t n = P.n;
+    const uint32_t nblk = P.nblk, nseg = P.nseg;
     const uint32_t rowQsBytes = nblk * 16;
-    const uint32_t nPairs = d / 2;
-    const uint32_t pairBegin = (uint32_t)(((uint64_t)blockIdx.x * nPairs) / gridDim.x);
-    const uint32_t pairEnd = (uint32_t)(((uint64_t)(blockIdx.x + 1) * nPairs) / gridDim.x);
-    const uint32_t rowBase = pairBegin * 2, tileRows = (pairEnd - pairBegin) * 2;
-    const uint32_t SR = megaStageRows(n, m.stageBytes);
-    const uint32_t nFills = (tileRows + SR - 1) / SR;
+    uint32_t pairBegin, tileRows;
+    megaTile(P, pairBegin, tileRows);
+    const uint32_t rowBase = pairBegin * 2;
+    const uint32_t SR = P.stageRows;
     uint4 *planeA = sm.planeA, *planeB = sm.planeB;
     float *dxs = sm.dxs, *dx8 = sm.dx8, *partial = sm.partial, *red = sm.red;
 
@@ -123,20 +139,19 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, uint32_t d, uint
     stamp();   // prologue done
 
     // ---- main loop over this phase's fills ----
-    for (uint32_t f = 0; f < nFills; f++, fillIdx++) {
-        const uint32_t st = fillIdx % m.nStages;
-        const uint32_t r0 = f * SR;
+    const uint32_t gInc = P.gInc, segInc = P.segInc;
+    uint32_t rot = 0;   // (fill index * steps per full stage) mod 16: rotates the step -> warp assignment from fill to fill
+    for (uint32_t r0 = 0; r0 < tileRows; r0 += SR) {
+        const uint32_t st = ring.st;
         const uint32_t rows = min(SR, tileRows - r0);
-        const uint32_t nGroups = (rows + kRowsPerStep - 1) / kRowsPerStep;
-        const uint32_t nSteps = nGroups * nseg;
-        const uint8_t *stage = sm.ring + (size_t)st * m.stageBytes;
+        const uint32_t nSteps = ((rows + kRowsPerStep - 1) / kRowsPerStep) * nseg;
+        const uint8_t *stage = sm.ring + st * m.stageBytes;
         const uint4 *sq = reinterpret_cast<const uint4 *>(stage);
-        const uint16_t *ss = reinterpret_cast<const uint16_t *>(stage + (size_t)SR * rowQsBytes);
-        const uint32_t stepsPerFullStage = (SR / kRowsPerStep) * nseg;
-        const uint32_t firstStep = (warp + kConsumerWarps - (f * stepsPerFullStage) % kConsumerWarps) % kConsumerWarps;
-        mbarWait(&sm.fullBar[st], (fillIdx / m.nStages) & 1);
-        uint32_t g = firstStep / nseg, seg = firstStep - g * nseg;
-        const uint32_t gInc = kConsumerWarps / nseg, segInc = kConsumerWarps - gInc * nseg;
+        const uint16_t *ss = reinterpret_cast<const uint16_t *>(stage + SR * rowQsBytes);
+        const uint32_t firstStep = ((uint32_t)warp - rot) & (kConsumerWarps - 1);
+        rot = (rot + P.rotInc) & (kConsumerWarps - 1);
+        uint32_t g = (firstStep * P.recipNseg) >> 16, seg = firstStep - g * nseg;   // firstStep / nseg, firstStep % nseg
+        mbarWait(&sm.fullBar[st], ring.par);
         // two steps are processed together (independent dependency chains -> the LDS/IDP/SHFL latencies overlap)
         auto stepDot = [&](uint32_t g_, uint32_t seg_, float (&acc)[kRowsPerStep]) {
             const uint32_t blk = seg_ * 32 + lane;
@@ -194,6 +209,7 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, uint32_t d, uint
         }
         __syncwarp();
         if (lane == 0) mbarArrive(&sm.emptyBar[st]);
+        ring.advance(m.nStages);
     }
     consumerBarrier();
     stamp();   // main loop done
@@ -536,40 +552,41 @@ __global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_
         // =============================== producer: every weight matrix of the token, back to back ===============================
         if (lane == 0) {
             const uint64_t policy = policyEvictFirst();
-            uint32_t fillIdx = 0;
-            auto stream = [&](const uint8_t *qs, const uint8_t *sc, uint32_t d, uint32_t n) {
-                const uint32_t nblk = n / 32, rowQsBytes = nblk * 16, rowScBytes = nblk * 2;
-                const uint32_t nPairs = d / 2;
-                const uint32_t pairBegin = (uint32_t)(((uint64_t)blockIdx.x * nPairs) / gridDim.x);
-                const uint32_t pairEnd = (uint32_t)(((uint64_t)(blockIdx.x + 1) * nPairs) / gridDim.x);
-                const uint32_t rowBase = pairBegin * 2, tileRows = (pairEnd - pairBegin) * 2;
-                const uint32_t SR = megaStageRows(n, m.stageBytes);
-                for (uint32_t r0 = 0; r0 < tileRows; r0 += SR, fillIdx++) {
-                    const uint32_t st = fillIdx % m.nStages;
-                    if (fillIdx >= m.nStages) mbarWait(&sm.emptyBar[st], ((fillIdx / m.nStages) - 1) & 1);
+            RingPos pr{0u, 0u};
+            bool wrapped = false;   // every stage has been filled once: from now on wait for the consumers to free it
+            auto stream = [&](const uint8_t *qs, const uint8_t *sc, const MegaPhase &P) {
+                const uint32_t rowQsBytes = P.nblk * 16, rowScBytes = P.nblk * 2;
+                uint32_t pairBegin, tileRows;
+                megaTile(P, pairBegin, tileRows);
+                const uint32_t rowBase = pairBegin * 2, SR = P.stageRows;
+                for (uint32_t r0 = 0; r0 < tileRows; r0 += SR) {
+                    const uint32_t st = pr.st;
+                    if (wrapped) mbarWait(&sm.emptyBar[st], pr.par ^ 1u);
                     const uint32_t rows = min(SR, tileRows - r0);
                     const uint32_t bq = rows * rowQsBytes, bs = rows * rowScBytes;
-                    uint8_t *dst = sm.ring + (size_t)st * m.stageBytes;
+                    uint8_t *dst = sm.ring + st * m.stageBytes;
                     mbarExpectTx(&sm.fullBar[st], bq + bs);
                     tmaBulkLoad(dst, qs + (uint64_t)(rowBase + r0) * rowQsBytes, bq, &sm.fullBar[st], policy);
-                    tmaBulkLoad(dst + (size_t)SR * rowQsBytes, sc + (uint64_t)(rowBase + r0) * rowScBytes, bs, &sm.fullBar[st], policy);
+                    tmaBulkLoad(dst + SR * rowQsBytes, sc + (uint64_t)(rowBase + r0) * rowScBytes, bs, &sm.fullBar[st], policy);
+                    pr.advance(m.nStages);
+                    if (pr.st == 0) wrapped = true;
                 }
             };
             for (uint32_t l = 0; l < m.nLayers; l++) {
                 const MegaLayer &L = m.layers[l];
-                stream(L.qkvQs, L.qkvSc, qkvDim, m.dim);
-                stream(L.woQs, L.woSc, m.dim, qDim);
-                stream(L.w13Qs, L.w13Sc, 2 * m.ffDim, m.dim);
-                stream(L.w2Qs, L.w2Sc, m.dim, m.ffDim);
+                stream(L.qkvQs, L.qkvSc, m.ph[MP_QKV]);
+                stream(L.woQs, L.woSc, m.ph[MP_WO]);
+                stream(L.w13Qs, L.w13Sc, m.ph[MP_W13]);
+                stream(L.w2Qs, L.w2Sc, m.ph[MP_W2]);
             }
-            stream(m.wclsQs, m.wclsSc, m.vocab, m.dim);
+            stream(m.wclsQs, m.wclsSc, m.ph[MP_LOGITS]);
         }
         return;
     }
 
     // =============================== consumers ===============================
     unsigned int barTarget = 0;
-    uint32_t fillIdx = 0;
+    RingPos ring{0u, 0u};
     uint32_t slot = 0;
     auto stamp = [&]() { if (m.trace && blockIdx.x == 0 && tid == 0) m.trace[slot] = globalTimerNs(); slot++; };
     stamp();
@@ -594,7 +611,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_
         prefetchVec(L.norm1);
         prefetchVec(l + 1 < m.nLayers ? m.layers[l + 1].norm0 : m.finalNorm);
         stamp();
-        megaGemv<PRO_RMSNORM_, EPI_STORE_>(m, sm, qkvDim, m.dim, m.x, L.norm0, m.qkv, 0, fillIdx, tid, slot);
+        megaGemv<PRO_RMSNORM_, EPI_STORE_>(m, sm, m.ph[MP_QKV], m.x, L.norm0, m.qkv, 0, ring, tid, slot);
         stamp();
         gridBarrier(m.gridCounter, barTarget, tid);
         stamp();
@@ -602,20 +619,20 @@ __global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_
         stamp();
         gridBarrier(m.gridCounter, barTarget, tid);
         stamp();
-        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.dim, qDim, m.z, nullptr, m.x, 0, fillIdx, tid, slot);
+        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.ph[MP_WO], m.z, nullptr, m.x, 0, ring, tid, slot);
         stamp();
         gridBarrier(m.gridCounter, barTarget, tid);
         stamp();
-        megaGemv<PRO_RMSNORM_, EPI_SWIGLU_>(m, sm, 2 * m.ffDim, m.dim, m.x, L.norm1, m.h, 0, fillIdx, tid, slot);
+        megaGemv<PRO_RMSNORM_, EPI_SWIGLU_>(m, sm, m.ph[MP_W13], m.x, L.norm1, m.h, 0, ring, tid, slot);
         stamp();
         gridBarrier(m.gridCounter, barTarget, tid);
         stamp();
-        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.dim, m.ffDim, m.h, nullptr, m.x, 1, fillIdx, tid, slot);
+        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.ph[MP_W2], m.h, nullptr, m.x, 1, ring, tid, slot);
         stamp();
         gridBarrier(m.gridCounter, barTarget, tid);
     }
     stamp();
-    megaGemv<PRO_RMSNORM_, EPI_ARGMAX_>(m, sm, m.vocab, m.dim, m.x, m.finalNorm, m.logits, 0, fillIdx, tid, slot);
+    megaGemv<PRO_RMSNORM_, EPI_ARGMAX_>(m, sm, m.ph[MP_LOGITS], m.x, m.finalNorm, m.logits, 0, ring, tid, slot);
     stamp();
 }
 
@@ -654,6 +671,22 @@ int launchMegaDecode(MegaArgs m, int numSms, cudaStream_t stream) {
     if (stages > (uint32_t)kMaxStages) stages = kMaxStages;
     m.stageBytes = stageBytes;
     m.nStages = stages;
+    // per-phase geometry, so the device code contains no integer division
+    for (int i = 0; i < 5; i++) {
+        MegaPhase &P = m.ph[i];
+        P.d = ds[i]; P.n = dn[i];
+        P.nblk = dn[i] / 32;
+        P.nseg = (P.nblk + 31) / 32;
+        P.stageRows = megaStageRows(dn[i], stageBytes);
+        P.pairsQ = (ds[i] / 2) / grid;
+        P.pairsRem = (ds[i] / 2) % grid;
+        P.recipNseg = 65536u / P.nseg + 1u;                    // (s * recip) >> 16 == s / nseg for s < 16
+        P.gInc = (uint32_t)kConsumerWarps / P.nseg;
+        P.segInc = (uint32_t)kConsumerWarps - P.gInc * P.nseg;
+        P.rotInc = ((P.stageRows / kRowsPerStep) * P.nseg) % (uint32_t)kConsumerWarps;
+        for (uint32_t sft = 0; sft < (uint32_t)kConsumerWarps; sft++)
+            if (((sft * P.recipNseg) >> 16) != sft / P.nseg) return 1;
+    }
     const size_t smemBytes = fixedBytes + (size_t)stages * stageBytes;
     static size_t configured[2] = {0, 0};
     const int v = m.headDim == 128 ? 1 : 0;
