@@ -83,8 +83,18 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
     {
         const uint32_t nVec = n / 4;
         const float4 *x4 = reinterpret_cast<const float4 *>(in);
-        constexpr int kMaxVec = 8;                       // 8 float4 x 512 threads = 16384 elements
+        // plain phases: 8 float4 x 512 threads = 16384 elements; RMS-norm phases (n = dim <= 8192) hold the norm weights in the
+        // other half of that register budget, loaded together with x so only one L2 round trip sits on the critical path
+        constexpr int kMaxVec = PRO == PRO_RMSNORM_ ? 4 : 8;
         float4 xv[kMaxVec];
+        float4 wv[PRO == PRO_RMSNORM_ ? kMaxVec : 1];
+        if (PRO == PRO_RMSNORM_) {
+#pragma unroll
+            for (int k = 0; k < kMaxVec; k++) {
+                const uint32_t i = k * kConsumerThreads + tid;
+                wv[k] = i < nVec ? __ldg(reinterpret_cast<const float4 *>(normW) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
         float ss = 0.f;
 #pragma unroll
         for (int k = 0; k < kMaxVec; k++) {
@@ -106,7 +116,7 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
             const bool act = i < nVec;
             float4 v = xv[k];
             if (PRO == PRO_RMSNORM_ && act) {
-                const float4 w = reinterpret_cast<const float4 *>(normW)[i];
+                const float4 w = wv[PRO == PRO_RMSNORM_ ? k : 0];
                 v.x = w.x * (v.x * inv); v.y = w.y * (v.y * inv); v.z = w.z * (v.z * inv); v.w = w.w * (v.w * inv);
             }
             float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
@@ -646,7 +656,7 @@ int launchMegaDecode(MegaArgs m, int numSms, cudaStream_t stream) {
         if (n % 128) return 1;
         if (n > maxN) maxN = n;
     }
-    if (maxN > 8 * kConsumerThreads * 4) return 1;   // the activation vector is held in registers during the prologue
+    if (maxN > 8 * kConsumerThreads * 4 || m.dim > 4 * kConsumerThreads * 4) return 1;   // activation (+ norm) vectors live in registers during the prologue
     const uint32_t grid = (uint32_t)numSms;
     // partial buffer: rows of the largest tile x segments; also hosts the attention scratch (16 x HD + 32 floats)
     const uint32_t ds[5] = {qDim + 2 * m.nKvHeads * m.headDim, m.dim, 2 * m.ffDim, m.dim, m.vocab};
