@@ -56,6 +56,9 @@ def build_host(force: bool = False, verbose: bool = False) -> Path:
     out = host_lib_path()
     stamp = out.with_suffix(out.suffix + ".hash")
     flags = ["-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-Wno-sign-compare"]
+    if os.environ.get("DLLAMA_DEBUG") == "1":
+        # reference: `make DEBUG=1` => -g -fsanitize=address (Makefile:8-12). Run python with LD_PRELOAD=$(g++ -print-file-name=libasan.so).
+        flags = ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"] + flags[1:]
     digest = _hash_sources(sources + headers, " ".join(flags))
     with _lock:
         if not force and out.exists() and stamp.exists() and stamp.read_text() == digest:
@@ -88,6 +91,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     stamp = out.with_suffix(".so.hash")
     flags = [*NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC",
              "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+    if os.environ.get("DLLAMA_DEBUG") == "1":
+        flags = [f for f in flags if f not in ("-O3", "--use_fast_math")] + ["-O1", "-g"]   # device code stays optimised; tools/sanitize.sh
     digest = _hash_sources(sources + headers, " ".join(flags))
     with _lock:
         if not force and out.exists() and stamp.exists() and stamp.read_text() == digest:
