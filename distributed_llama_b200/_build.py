@@ -129,12 +129,39 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     return out
 
 
+def native_bin_path() -> Path:
+    return PKG_DIR / "dllama-native"
+
+
+def build_native(force: bool = False, verbose: bool = False) -> Path:
+    """The Python-free front end: csrc/app (CLI + engine driver) + csrc/host (formats, tokenizer, sampler) linked against
+    _cuda.so and the CUDA runtime. Reference counterpart: the `dllama` make target (Makefile:40-60)."""
+    cuda_so = build_cuda(force, verbose)
+    sources = sorted((CSRC / "app").glob("*.cpp")) + [CSRC / "host" / n for n in ("quants.cpp", "model_format.cpp", "text.cpp")]
+    headers = sorted((CSRC / "app").glob("*.hpp")) + sorted((CSRC / "host").glob("*.hpp")) + [CSRC / "cuda" / "engine_api.h"]
+    out = native_bin_path()
+    stamp = out.with_suffix(".hash")
+    cuda_home = Path(nvcc_path()).resolve().parent.parent
+    flags = ["-O2", "-std=c++17", "-Wall", "-Wno-sign-compare", f"-I{cuda_home}/include"]
+    link = [f"-L{PKG_DIR}", "-l:_cuda.so", f"-L{cuda_home}/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{cuda_home}/lib64"]
+    digest = _hash_sources(sources + headers + [cuda_so.with_suffix(".so.hash")], " ".join(flags + link))
+    with _lock:
+        if not force and out.exists() and stamp.exists() and stamp.read_text() == digest:
+            return out
+        tmp = out.with_suffix(".tmp")
+        log = _run(["g++", *flags, *map(str, sources), *link, "-o", str(tmp)])
+        if verbose and log:
+            print(log)
+        os.replace(tmp, out)
+        stamp.write_text(digest)
+    return out
+
+
 def build_all(force: bool = False, verbose: bool = False):
-    return build_host(force, verbose), build_cuda(force, verbose)
+    return build_host(force, verbose), build_cuda(force, verbose), build_native(force, verbose)
 
 
 if __name__ == "__main__":
     force = "--force" in sys.argv
-    h, c = build_all(force=force, verbose="-v" in sys.argv)
-    print(h)
-    print(c)
+    for path in build_all(force=force, verbose="-v" in sys.argv):
+        print(path)

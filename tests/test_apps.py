@@ -124,3 +124,16 @@ def test_dllama_api_server(tmp_models):
         p.terminate()
         out = p.communicate(timeout=30)[0]
     assert "🐤 Found naive cache" in out, out[-2000:]
+
+
+def test_native_cli_arg_surface():
+    """dllama-native (C++): usage text, unknown flags / modes and missing files fail with the reference's message + exit code 1."""
+    exe = os.path.join(ROOT, "dllama-native")
+    r = subprocess.run([exe, "--help"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "Usage: dllama-native" in r.stdout
+    for argv, msg in ((["inference", "--bogus", "1"], "Unknown option"), (["train", "--model", "a", "--tokenizer", "b"], "Unsupported mode"),
+                      (["inference", "--tokenizer", "b"], "Model is required"),
+                      (["inference", "--model", "/nonexistent.m", "--tokenizer", "b", "--workers", "1.2.3.4:9", "5.6.7.8:9", "--nthreads", "4"],
+                       "Cannot open model file")):
+        r = subprocess.run([exe] + argv, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 1 and "🚨 Critical error" in r.stdout and msg in r.stdout, r.stdout
