@@ -129,36 +129,43 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     return out
 
 
-def native_bin_path() -> Path:
-    return PKG_DIR / "dllama-native"
+NATIVE_BINARIES = {"dllama-native": "dllama_main.cpp", "dllama-api-native": "dllama_api_main.cpp"}
 
 
-def build_native(force: bool = False, verbose: bool = False) -> Path:
-    """The Python-free front end: csrc/app (CLI + engine driver) + csrc/host (formats, tokenizer, sampler) linked against
-    _cuda.so and the CUDA runtime. Reference counterpart: the `dllama` make target (Makefile:40-60)."""
+def native_bin_path(name: str = "dllama-native") -> Path:
+    return PKG_DIR / name
+
+
+def build_native(force: bool = False, verbose: bool = False):
+    """The Python-free front ends: csrc/app (CLI, API server, engine driver) + csrc/host (formats, tokenizer, sampler) linked
+    against _cuda.so and the CUDA runtime. Reference counterparts: the `dllama` / `dllama-api` make targets (Makefile:40-66)."""
     cuda_so = build_cuda(force, verbose)
-    sources = sorted((CSRC / "app").glob("*.cpp")) + [CSRC / "host" / n for n in ("quants.cpp", "model_format.cpp", "text.cpp")]
-    headers = sorted((CSRC / "app").glob("*.hpp")) + sorted((CSRC / "host").glob("*.hpp")) + [CSRC / "cuda" / "engine_api.h"]
-    out = native_bin_path()
-    stamp = out.with_suffix(".hash")
+    app = CSRC / "app"
+    common = [app / "native_engine.cpp", app / "api_server.cpp"] + [CSRC / "host" / n for n in ("quants.cpp", "model_format.cpp", "text.cpp")]
+    headers = sorted(app.glob("*.hpp")) + sorted((CSRC / "host").glob("*.hpp")) + [CSRC / "cuda" / "engine_api.h"]
     cuda_home = Path(nvcc_path()).resolve().parent.parent
     flags = ["-O2", "-std=c++17", "-Wall", "-Wno-sign-compare", f"-I{cuda_home}/include"]
-    link = [f"-L{PKG_DIR}", "-l:_cuda.so", f"-L{cuda_home}/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{cuda_home}/lib64"]
-    digest = _hash_sources(sources + headers + [cuda_so.with_suffix(".so.hash")], " ".join(flags + link))
-    with _lock:
-        if not force and out.exists() and stamp.exists() and stamp.read_text() == digest:
-            return out
-        tmp = out.with_suffix(".tmp")
-        log = _run(["g++", *flags, *map(str, sources), *link, "-o", str(tmp)])
-        if verbose and log:
-            print(log)
-        os.replace(tmp, out)
-        stamp.write_text(digest)
-    return out
+    link = [f"-L{PKG_DIR}", "-l:_cuda.so", f"-L{cuda_home}/lib64", "-lcudart", "-lpthread", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{cuda_home}/lib64"]
+    outs = []
+    for name, main_src in NATIVE_BINARIES.items():
+        sources = [app / main_src] + common
+        out = native_bin_path(name)
+        stamp = out.with_suffix(".hash")
+        digest = _hash_sources(sources + headers + [cuda_so.with_suffix(".so.hash")], " ".join(flags + link))
+        with _lock:
+            if force or not out.exists() or not stamp.exists() or stamp.read_text() != digest:
+                tmp = out.with_suffix(".tmp")
+                log = _run(["g++", *flags, *map(str, sources), *link, "-o", str(tmp)])
+                if verbose and log:
+                    print(log)
+                os.replace(tmp, out)
+                stamp.write_text(digest)
+        outs.append(out)
+    return outs
 
 
 def build_all(force: bool = False, verbose: bool = False):
-    return build_host(force, verbose), build_cuda(force, verbose), build_native(force, verbose)
+    return [build_host(force, verbose), build_cuda(force, verbose), *build_native(force, verbose)]
 
 
 if __name__ == "__main__":

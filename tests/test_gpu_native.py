@@ -45,3 +45,44 @@ def test_native_perplexity_and_sampling(tmp_models):
         assert s.returncode == 0, s.stdout[-2000:]
         runs.append(_pred(s.stdout))
     assert runs[0] == runs[1] and len(runs[0]) >= 8
+
+
+def test_native_api_server_on_gpu(tmp_models):
+    """dllama-api-native: one non-stream and one streamed completion against the real engine."""
+    import http.client
+    import json
+    import socket
+    import time
+    m, t = tmp_models["tiny-llama31"]
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    proc = subprocess.Popen([os.path.join(ROOT, "dllama-api-native"), "--model", m, "--tokenizer", t, "--host", "127.0.0.1", "--port", str(port),
+                             "--max-requests", "3", "--temperature", "0"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        for _ in range(600):
+            try:
+                socket.create_connection(("127.0.0.1", port), timeout=0.2).close()      # uses one request slot
+                break
+            except OSError:
+                time.sleep(0.1)
+        body = {"messages": [{"role": "user", "content": "Hello there"}], "max_tokens": 16, "temperature": 0}
+        outs = []
+        for stream in (False, True):
+            c = http.client.HTTPConnection("127.0.0.1", port, timeout=120)
+            c.request("POST", "/v1/chat/completions", body=json.dumps(dict(body, stream=stream)), headers={"Content-Type": "application/json"})
+            r = c.getresponse()
+            data = r.read().decode("utf-8")
+            assert r.status == 200
+            if stream:
+                ev = [e for e in data.split("\r\n\r\n") if e.startswith("data: ")]
+                assert ev[-1] == "data: [DONE]"
+                outs.append("".join(json.loads(e[6:])["choices"][0].get("delta", {}).get("content", "") for e in ev[:-1]))
+            else:
+                j = json.loads(data)
+                assert j["usage"]["completion_tokens"] >= 1
+                outs.append(j["choices"][0]["message"]["content"])
+        assert outs[0] == outs[1]          # greedy: the streamed text equals the non-streamed one (same prompt, cache cleared by mismatch)
+    finally:
+        try:
+            proc.communicate(timeout=20)
+        except subprocess.TimeoutExpired:
+            proc.kill()
