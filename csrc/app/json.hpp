@@ -110,6 +110,7 @@ private:
                         if (lo >= 0xDC00 && lo <= 0xDFFF) cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
                         else { utf8(out, 0xFFFD); cp = lo; }
                     }
+                    if (cp >= 0xD800 && cp <= 0xDFFF) cp = 0xFFFD;   // unpaired surrogate
                     utf8(out, cp);
                     break;
                 }

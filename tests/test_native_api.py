@@ -116,3 +116,10 @@ def test_bad_requests_do_not_kill_the_server(stub):
     assert st == 200
     out, _ = proc.communicate(timeout=10)
     assert "JSON parse error" in out and "missing key" in out
+
+
+def test_json_reader_writer(tmp_path):
+    exe = str(tmp_path / "json_test")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", os.path.join(ROOT, "tests", "native", "json_test.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "JSON_TEST_OK" in r.stdout, r.stdout
