@@ -22,11 +22,24 @@ def _load_tool(name):
 def _hf_model(kind, tmp_path):
     transformers = pytest.importorskip("transformers")
     torch.manual_seed(0)
-    if kind == "llama":
+    if kind in ("llama", "llama31"):
+        extra = {}
+        if kind == "llama31":   # Llama-3.1 frequency rescaling (reference scaleFrequencyLlama3, src/nn/nn-core.cpp:326-340)
+            extra = dict(rope_parameters={"rope_type": "llama3", "rope_theta": 500000.0, "factor": 8.0, "low_freq_factor": 1.0,
+                                          "high_freq_factor": 4.0, "original_max_position_embeddings": 64})
+        else:
+            extra = dict(rope_parameters={"rope_type": "default", "rope_theta": 10000.0})
         cfg = transformers.LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
                                        num_key_value_heads=2, vocab_size=300, max_position_embeddings=128, rms_norm_eps=1e-5,
-                                       rope_theta=10000.0, tie_word_embeddings=False, hidden_act="silu")
+                                       tie_word_embeddings=False, hidden_act="silu", **extra)
         model = transformers.LlamaForCausalLM(cfg)
+    elif kind == "qwen3_moe":
+        cfg = transformers.Qwen3MoeConfig(hidden_size=128, intermediate_size=256, moe_intermediate_size=64, num_hidden_layers=2,
+                                          num_attention_heads=4, num_key_value_heads=2, head_dim=64, vocab_size=300,
+                                          max_position_embeddings=128, rms_norm_eps=1e-6, rope_theta=1000000.0, tie_word_embeddings=False,
+                                          hidden_act="silu", num_experts=8, num_experts_per_tok=2, norm_topk_prob=True,
+                                          decoder_sparse_step=1, mlp_only_layers=[])
+        model = transformers.Qwen3MoeForCausalLM(cfg)
     else:
         cfg = transformers.Qwen3Config(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
                                        num_key_value_heads=2, head_dim=64, vocab_size=300, max_position_embeddings=128,
@@ -38,7 +51,7 @@ def _hf_model(kind, tmp_path):
     return model, str(d)
 
 
-@pytest.mark.parametrize("kind", ["llama", "qwen3"])
+@pytest.mark.parametrize("kind", ["llama", "llama31", "qwen3", "qwen3_moe"])
 def test_convert_hf_matches_transformers(kind, tmp_path):
     from distributed_llama_b200.formats import ModelFile
     from distributed_llama_b200.models.reference import OracleModel
@@ -48,6 +61,10 @@ def test_convert_hf_matches_transformers(kind, tmp_path):
     conv.convert(folder, "f32", out)
     mf = ModelFile(out)
     assert mf.header.dim == 128 and mf.header.n_layers == 2 and mf.header.vocab_size == 300
+    if kind == "llama31":
+        assert mf.header.rope_type == 2 and mf.header.rope_scaling_factor == 8.0 and mf.header.rope_scaling_orig_max_seq_len == 64
+    if kind == "qwen3_moe":
+        assert mf.header.n_experts == 8 and mf.header.n_active_experts == 2 and mf.header.moe_hidden_dim == 64
     toks = [5, 17, 250, 9, 44, 101, 7, 299, 12]
     with torch.no_grad():
         ref = model(torch.tensor([toks])).logits[0]

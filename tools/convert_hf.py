@@ -41,11 +41,12 @@ def header_from_config(cfg: dict, weights_float_type: int) -> Dict[str, int]:
     act = {"gelu": 0, "silu": 1}.get(cfg["hidden_act"])
     if act is None:
         raise ValueError(f"Unsupported hidden act: {cfg['hidden_act']}")
+    # the expert count is saved as `num_experts` by the published Qwen3-MoE checkpoints and as `num_local_experts` by transformers >= 5
     p = {"version": 0, "arch_type": ARCH_BY_MODEL_TYPE[mt], "hidden_act": act, "dim": cfg["hidden_size"],
          "hidden_dim": cfg["intermediate_size"], "n_layers": cfg["num_hidden_layers"], "n_heads": cfg["num_attention_heads"],
          "n_kv_heads": cfg["num_key_value_heads"], "weights_float_type": weights_float_type,
          "max_seq_len": cfg["max_position_embeddings"], "vocab_size": cfg["vocab_size"],
-         "n_experts": int(cfg.get("num_experts") or 0), "n_active_experts": int(cfg.get("num_experts_per_tok") or 0)}
+         "n_experts": int(cfg.get("num_experts") or cfg.get("num_local_experts") or 0), "n_active_experts": int(cfg.get("num_experts_per_tok") or 0)}
     rope_params = cfg.get("rope_parameters") or {}
     theta = cfg.get("rope_theta", rope_params.get("rope_theta"))
     if theta is not None:
