@@ -68,15 +68,20 @@ def download_file(urls, path: str):
                 try:
                     req = Request(url, headers={"Range": f"bytes={offset - start_offset}-"} if offset > start_offset else {})
                     with urlopen(req) as resp:
+                        expected = resp.headers.get("Content-Length")
+                        received = 0
                         while True:
                             chunk = resp.read(1 << 16)
                             if not chunk:
                                 break
                             f.write(chunk)
                             offset += len(chunk)
+                            received += len(chunk)
                             if time.time() - last > 1:
                                 sys.stdout.write(f"\rDownloaded {offset // 1024} kB")
                                 last = time.time()
+                        if expected is not None and received < int(expected):   # connection dropped mid-body: resume, do not truncate
+                            raise ConnectionError(f"short read: {received} of {expected} bytes")
                     break
                 except Exception as e:   # resume from the bytes already on disk
                     attempts -= 1
