@@ -90,3 +90,49 @@ def test_llama3_tokenizer_converter(tmp_path):
     assert tk.bos_id == len(pieces) and tk.vocab_size == len(pieces) + 256 and tk.piece(tk.eos_ids[1]) == b"<|eot_id|>"
     ids = tk.encode("hello<|eot_id|>", True, True)
     assert [tk.piece(i) for i in ids] == [b"<|begin_of_text|>", b"hello", b"<|eot_id|>"]
+
+
+def test_convert_meta_checkpoint_two_shards(tmp_path):
+    """tools/convert_llama.py: a 2-way model-parallel Meta checkpoint (consolidated.00/01.pth + params.json), derived from a tiny
+    HF Llama, must convert to a `.m` whose oracle logits match the HF model — checks the per-tensor concatenation axes."""
+    from distributed_llama_b200.formats import ModelFile
+    from distributed_llama_b200.models.reference import OracleModel
+    model, _ = _hf_model("llama", tmp_path)
+    hf_conv = _load_tool("convert_hf")
+    sd = model.state_dict()
+    n_heads, n_kv, n_layers = 4, 2, 2
+    meta = {"tok_embeddings.weight": sd["model.embed_tokens.weight"], "norm.weight": sd["model.norm.weight"], "output.weight": sd["lm_head.weight"]}
+    for l in range(n_layers):
+        pre, dst = f"model.layers.{l}.", f"layers.{l}."
+        meta[dst + "attention.wq.weight"] = hf_conv.to_interleaved(sd[pre + "self_attn.q_proj.weight"], n_heads)   # Meta keeps rotary pairs adjacent
+        meta[dst + "attention.wk.weight"] = hf_conv.to_interleaved(sd[pre + "self_attn.k_proj.weight"], n_kv)
+        meta[dst + "attention.wv.weight"] = sd[pre + "self_attn.v_proj.weight"]
+        meta[dst + "attention.wo.weight"] = sd[pre + "self_attn.o_proj.weight"]
+        meta[dst + "feed_forward.w1.weight"] = sd[pre + "mlp.gate_proj.weight"]
+        meta[dst + "feed_forward.w2.weight"] = sd[pre + "mlp.down_proj.weight"]
+        meta[dst + "feed_forward.w3.weight"] = sd[pre + "mlp.up_proj.weight"]
+        meta[dst + "attention_norm.weight"] = sd[pre + "input_layernorm.weight"]
+        meta[dst + "ffn_norm.weight"] = sd[pre + "post_attention_layernorm.weight"]
+    folder = tmp_path / "meta"
+    folder.mkdir()
+    row_parallel = ("wo.weight", "w2.weight", "tok_embeddings.weight")
+    for r in range(2):
+        shard = {}
+        for k, v in meta.items():
+            v = v.detach().clone()
+            if v.dim() == 1:
+                shard[k] = v
+            else:
+                axis = 1 if k.endswith(row_parallel) else 0
+                shard[k] = v.chunk(2, dim=axis)[r].contiguous()
+        torch.save(shard, str(folder / f"consolidated.{r:02d}.pth"))
+    (folder / "params.json").write_text(json.dumps({"dim": 128, "n_layers": n_layers, "n_heads": n_heads, "n_kv_heads": n_kv, "vocab_size": 300,
+                                                    "max_seq_len": 128, "norm_eps": 1e-05, "rope_theta": 10000.0}))
+    out = str(tmp_path / "meta.m")
+    _load_tool("convert_llama").convert(str(folder), "f32", out)
+    mf = ModelFile(out)
+    assert mf.header.ff_dim == 256 and mf.header.n_kv_heads == 2 and mf.header.rope_theta == 10000.0
+    toks = [5, 17, 250, 9, 44, 101, 7, 299, 12]
+    with torch.no_grad():
+        ref = model(torch.tensor([toks])).logits[0]
+    assert (OracleModel(mf).forward(toks, 0) - ref).abs().max().item() < 2e-3
