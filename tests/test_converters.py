@@ -136,3 +136,70 @@ def test_convert_meta_checkpoint_two_shards(tmp_path):
     with torch.no_grad():
         ref = model(torch.tensor([toks])).logits[0]
     assert (OracleModel(mf).forward(toks, 0) - ref).abs().max().item() < 2e-3
+
+
+_CORPUS = ["the quick brown fox jumps over the lazy dog " * 3, "hello world, hello there; héllo wörld ✓ emoji 😀 test",
+           "numbers 12345 67890 and symbols !@#$%^&*()", "The model generates tokens one at a time."] * 20
+
+
+def test_hf_fast_tokenizer_converter_matches_tokenizers(tmp_path):
+    """tools/convert_tokenizer_hf.py on a byte-level BPE tokenizer trained in-process: vocabulary bytes (GPT-2 alphabet
+    un-mapping), scores (= -id), bos/eos resolution from config.json, chat template; the native encoder reproduces the
+    `tokenizers` ids and the streaming decoder reproduces the text."""
+    tk = pytest.importorskip("tokenizers")
+    from tokenizers import Tokenizer, decoders, models, pre_tokenizers, trainers
+    from distributed_llama_b200 import host
+    d = tmp_path / "hf_tok"
+    d.mkdir()
+    tok = Tokenizer(models.BPE())
+    tok.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False)
+    tok.decoder = decoders.ByteLevel()
+    tok.train_from_iterator(_CORPUS, trainers.BpeTrainer(vocab_size=420, special_tokens=[], initial_alphabet=pre_tokenizers.ByteLevel.alphabet()))
+    tok.add_special_tokens(["<|begin_of_text|>", "<|end_of_text|>", "<|eot_id|>"])
+    tok.save(str(d / "tokenizer.json"))
+    bos, eos = tok.token_to_id("<|begin_of_text|>"), tok.token_to_id("<|end_of_text|>")
+    template = "{% for m in messages %}<|start_header_id|>{{m['role']}}<|end_header_id|>{% endfor %}"
+    (d / "tokenizer_config.json").write_text(json.dumps({"tokenizer_class": "PreTrainedTokenizerFast", "add_bos_token": True, "chat_template": template}))
+    (d / "config.json").write_text(json.dumps({"bos_token_id": bos, "eos_token_id": [eos, eos + 1]}))
+    out = str(tmp_path / "hf.t")
+    _load_tool("convert_tokenizer_hf").convert(str(d), out)
+    T = host().Tokenizer(out)
+    assert T.vocab_size == tok.get_vocab_size() and list(T.eos_ids) == [eos, eos + 1] and T.chat_template == template.encode()
+    for text in ["the quick brown fox", "hello world", "héllo wörld ✓ 😀", "12345 tokens!", "Theseus unknownword zzz", " leading space"]:
+        ids = tok.encode(text).ids
+        assert list(T.encode(text, False, False)) == ids, text
+        T.reset_decoder()
+        assert b"".join(T.decode(i) for i in ids).decode("utf-8") == text
+    # with isStart the BOS id is prepended; special tokens are matched literally when asked to
+    assert list(T.encode("hello", True, False))[0] == bos
+    assert eos in list(T.encode("hello<|end_of_text|>", False, True))
+
+
+def test_sentencepiece_tokenizer_converters(tmp_path):
+    """SentencePiece route of convert_tokenizer_hf.py and convert_tokenizer_llama2.py: `▁` -> space, <0xNN> byte pieces, scores kept."""
+    spm = pytest.importorskip("sentencepiece")
+    from distributed_llama_b200 import host
+    d = tmp_path / "sp_tok"
+    d.mkdir()
+    corpus = d / "corpus.txt"
+    corpus.write_text("\n".join(_CORPUS))
+    spm.SentencePieceTrainer.train(input=str(corpus), model_prefix=str(d / "tokenizer"), vocab_size=400, model_type="bpe", byte_fallback=True,
+                                   character_coverage=1.0, bos_id=1, eos_id=2, unk_id=0, pad_id=-1, minloglevel=2)
+    sp = spm.SentencePieceProcessor(model_file=str(d / "tokenizer.model"))
+    (d / "tokenizer_config.json").write_text(json.dumps({"tokenizer_class": "LlamaTokenizer", "add_bos_token": True}))
+    out_hf, out_l2 = str(tmp_path / "sp_hf.t"), str(tmp_path / "sp_l2.t")
+    _load_tool("convert_tokenizer_hf").convert(str(d), out_hf)
+    _load_tool("convert_tokenizer_llama2").convert(str(d), out_l2)
+    H = host()
+    for path in (out_hf, out_l2):
+        T = H.Tokenizer(path)
+        assert T.vocab_size == sp.vocab_size() and list(T.eos_ids) == [2]
+        for text in ["the quick brown fox", "hello wörld ✓"]:
+            ids = sp.encode(text)
+            T.reset_decoder()
+            got = b"".join(T.decode(i) for i in ids).decode("utf-8")
+            assert got.strip() == text            # sentencepiece's dummy prefix becomes a leading space
+    # scores survive the conversion (they drive the merge order of the runtime encoder)
+    data = H.read_tokenizer_file(out_hf) if hasattr(H, "read_tokenizer_file") else None
+    if data is not None:
+        assert abs(data.scores[10] - sp.get_score(10)) < 1e-6

@@ -40,7 +40,7 @@ def from_fast_tokenizer(folder: str):
             raw += bytes([u2b[ch]]) if ch in u2b else ch.encode("utf-8")
         tokens.append(bytes(raw))
         scores.append(-float(i))
-    bos, eos = tk.bos_token_id, ([tk.eos_token_id] if tk.eos_token_id else None)
+    bos, eos = tk.bos_token_id, ([tk.eos_token_id] if tk.eos_token_id is not None else None)
     if bos is None or eos is None:
         with open(os.path.join(folder, "config.json")) as f:
             cfg = json.load(f)
