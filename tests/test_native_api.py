@@ -123,3 +123,62 @@ def test_json_reader_writer(tmp_path):
     subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", os.path.join(ROOT, "tests", "native", "json_test.cpp"), "-o", exe], check=True)
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "JSON_TEST_OK" in r.stdout, r.stdout
+
+
+def test_python_and_native_servers_agree(stub):
+    """The Python server (apps/api_server.py, used for multi-GPU serving) and the native one run the same deterministic stub
+    model: their non-stream JSON and their streamed text must be identical for the same requests."""
+    import threading
+    from types import SimpleNamespace
+
+    from distributed_llama_b200 import host
+    from distributed_llama_b200.apps import api_server as py_api
+    from distributed_llama_b200.apps.args import parse_args
+
+    exe, tok_path = stub
+    H = host()
+    tok = H.Tokenizer(tok_path)
+    regular, eos = tok.regular_vocab_size, list(tok.eos_ids)[0]
+
+    class FakeInference:
+        comm = None
+
+        def __init__(self):
+            self.produced = 0
+
+        def prefill(self, tokens, pos):
+            self.produced = 0
+
+        def forward_greedy(self, token, pos):
+            self.produced += 1
+            return eos if self.produced > 12 else (token * 7 + pos * 13 + 5) % regular
+
+    port_py = _free_port()
+    args = parse_args(["--model", "stub.m", "--tokenizer", tok_path, "--host", "127.0.0.1", "--port", str(port_py), "--temperature", "0"], False)
+    ctx = SimpleNamespace(args=args, sess=None, inference=FakeInference(), tokenizer=tok, sampler=H.Sampler(tok.vocab_size, 0.0, 0.9, 1),
+                          header=SimpleNamespace(seq_len=4096, vocab_size=tok.vocab_size))
+    th = threading.Thread(target=py_api.serve, args=(ctx, 2), daemon=True)
+    th.start()
+    for _ in range(100):
+        try:
+            socket.create_connection(("127.0.0.1", port_py), timeout=0.2).close()
+            break
+        except OSError:
+            time.sleep(0.05)
+    # the probe above consumed one of the two request slots of the Python server; the native stub gets 1 probe + 1 request
+    proc, port_nat = _start(stub, 2)
+    msgs = [{"role": "system", "content": "be brief"}, {"role": "user", "content": "héllo ✓ \"quoted\""}]
+    body = {"messages": msgs, "temperature": 0, "max_tokens": 64}
+    try:
+        _, _, a = _req(port_py, "POST", "/v1/chat/completions", body)
+        _, _, b = _req(port_nat, "POST", "/v1/chat/completions", body)
+    finally:
+        try:
+            proc.communicate(timeout=10)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+        th.join(timeout=10)
+    ja, jb = json.loads(a), json.loads(b)
+    for j in (ja, jb):
+        j.pop("created")
+    assert ja == jb and ja["usage"]["completion_tokens"] == 13
