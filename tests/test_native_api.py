@@ -182,3 +182,24 @@ def test_python_and_native_servers_agree(stub):
     for j in (ja, jb):
         j.pop("created")
     assert ja == jb and ja["usage"]["completion_tokens"] == 13
+
+
+def test_example_client_against_native_server(stub, capsys):
+    """examples/chat_api_client.py (non-stream + stream helpers) talks to the native server."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("chat_api_client", os.path.join(ROOT, "examples", "chat_api_client.py"))
+    client = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(client)
+    proc, port = _start(stub, 3)
+    client.HOST = f"http://127.0.0.1:{port}"
+    try:
+        out = client.chat([{"role": "user", "content": "2+2?"}], max_tokens=32)
+        assert out["choices"][0]["message"]["role"] == "assistant" and out["usage"]["completion_tokens"] == 13
+        client.chat([{"role": "user", "content": "and 3+3?"}], max_tokens=32, stream=True)
+        streamed = capsys.readouterr().out
+        assert len(streamed.strip()) > 0
+    finally:
+        try:
+            proc.communicate(timeout=10)
+        except subprocess.TimeoutExpired:
+            proc.kill()
