@@ -265,7 +265,75 @@ def ref_binary():
     return exe, None
 
 
+def _cpu_topology():
+    """(logical CPUs this process may use, hardware threads per core) — the reference spins one busy thread per --nthreads."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except Exception:
+        cpus = list(range(os.cpu_count() or 8))
+    tpc = 1
+    try:
+        sib = open(f"/sys/devices/system/cpu/cpu{cpus[0]}/topology/thread_siblings_list").read().strip()
+        tpc = max(1, len([x for part in sib.split(",") for x in ([part] if "-" not in part else range(int(part.split("-")[0]), int(part.split("-")[1]) + 1))]))
+    except Exception:
+        pass
+    return cpus, tpc
+
+
+def _run_reference_once(exe, args, model_path, tok_path, n, threads, steps, warm, cpus, timeout):
+    """One run of the stock reference CLI: root + (n-1) `dllama worker` processes on 127.0.0.1, each pinned to its own CPU set."""
+    workers, ports = [], []
+    per = max(1, len(cpus) // n)
+
+    def pin(i):
+        mine = cpus[i * per:(i + 1) * per] or cpus
+        return lambda: os.sched_setaffinity(0, mine)
+    try:
+        for w in range(n - 1):
+            port = 9999 - w
+            ports.append(port)
+            workers.append(subprocess.Popen([exe, "worker", "--port", str(port), "--nthreads", str(threads)],
+                                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, preexec_fn=pin(w + 1)))
+        if workers:
+            time.sleep(2.0)
+        prompt = " ".join(["hello"] * max(1, args.prompt_len - 1))
+        total_steps = args.prompt_len + steps + warm + 8
+        cmd = [exe, "inference", "--model", model_path, "--tokenizer", tok_path, "--buffer-float-type", "q80",
+               "--prompt", prompt, "--steps", str(total_steps), "--nthreads", str(threads), "--temperature", "0",
+               "--max-seq-len", str(max(args.max_seq_len, total_steps + 8))]
+        if ports:
+            cmd += ["--workers"] + [f"127.0.0.1:{p}" for p in ports]
+        t0 = time.time()
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, preexec_fn=pin(0))
+        wall = time.time() - t0
+        text = r.stdout
+        pred = [int(m.group(1)) + int(m.group(2)) for m in re.finditer(r"Pred\s*(\d+) ms Sync\s*(\d+) ms", text)]
+        evals = [(int(m.group(1)) + int(m.group(2)), int(m.group(3))) for m in re.finditer(r"Eval\s*(\d+) ms Sync\s*(\d+) ms.*\((\d+) tokens\)", text)]
+        m_pred = re.search(r"Prediction\s*\n\s*nTokens: (\d+)\s*\n\s*tokens/s: ([\d.]+) \(([\d.]+) ms/tok\)", text)
+        if r.returncode != 0 or not m_pred:
+            return {"error": "reference run failed: " + text[-300:].replace("\n", " ")}
+        timed = pred[warm: warm + steps] if len(pred) >= warm + steps else pred[warm:]
+        ms_per_step = sum(timed) / max(1, len(timed)) if timed else float(m_pred.group(3))
+        if ms_per_step <= 0:     # ms granularity of the reference's printout; fall back to its own summary
+            ms_per_step = float(m_pred.group(3))
+        return {"ms_per_step": ms_per_step, "n_timed": len(timed) or int(m_pred.group(1)), "eval_ms": sum(e[0] for e in evals),
+                "summary_tok_s": float(m_pred.group(2)), "wall": wall, "threads": threads}
+    except subprocess.TimeoutExpired:
+        return {"error": "reference run timed out"}
+    finally:
+        for p in workers:
+            try:
+                p.kill()
+                p.wait(timeout=5)
+            except Exception:
+                pass
+
+
 def run_reference(args):
+    """Reference arm: the UNMODIFIED reference tree (baseline/_ref/distributed-llama), built with its own Makefile, driven through
+    its own CLI. The only thing chosen here is how it is launched: `--nthreads` is swept over the power-of-two counts that fit the
+    physical cores available to each of the n processes (short probe runs), processes are pinned to disjoint CPU sets, and the
+    best configuration is then timed on the full step count."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         # ranks other than 0 only exist because the driver launches both arms the same way
@@ -294,59 +362,41 @@ def run_reference(args):
         return finish({"impl": "reference", "unavailable": err})
     model_path, tok_path = ensure_model(args.model)
     n = args.gpus
-    cores = os.cpu_count() or 8
-    threads = max(1, min(64, cores // n))
-    # power-of-two thread count keeps the reference's work split even
-    threads = 1 << (threads.bit_length() - 1)
-    workers, ports = [], []
-    try:
-        for w in range(n - 1):
-            port = 9999 - w
-            ports.append(port)
-            workers.append(subprocess.Popen([exe, "worker", "--port", str(port), "--nthreads", str(threads)],
-                                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
-        if workers:
-            time.sleep(2.0)
-        prompt = " ".join(["hello"] * max(1, args.prompt_len - 1))
-        total_steps = args.prompt_len + args.steps + max(args.warmup, 3) + 8
-        cmd = [exe, "inference", "--model", model_path, "--tokenizer", tok_path, "--buffer-float-type", "q80",
-               "--prompt", prompt, "--steps", str(total_steps), "--nthreads", str(threads), "--temperature", "0",
-               "--max-seq-len", str(max(args.max_seq_len, total_steps + 8))]
-        if ports:
-            cmd += ["--workers"] + [f"127.0.0.1:{p}" for p in ports]
-        t0 = time.time()
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=args.ref_timeout)
-        wall = time.time() - t0
-        text = r.stdout
-        pred = [int(m.group(1)) + int(m.group(2)) for m in re.finditer(r"Pred\s*(\d+) ms Sync\s*(\d+) ms", text)]
-        evals = [(int(m.group(1)) + int(m.group(2)), int(m.group(3))) for m in re.finditer(r"Eval\s*(\d+) ms Sync\s*(\d+) ms.*\((\d+) tokens\)", text)]
-        m_pred = re.search(r"Prediction\s*\n\s*nTokens: (\d+)\s*\n\s*tokens/s: ([\d.]+) \(([\d.]+) ms/tok\)", text)
-        if r.returncode != 0 or not m_pred:
-            return finish({"impl": "reference", "unavailable": "reference run failed: " + text[-300:].replace("\n", " ")})
-        warm = max(args.warmup, 3)
-        timed = pred[warm: warm + args.steps] if len(pred) >= warm + args.steps else pred[warm:]
-        ms_per_step = sum(timed) / max(1, len(timed)) if timed else float(m_pred.group(3))
-        if ms_per_step <= 0:     # ms granularity of the reference's printout; fall back to its own summary
-            ms_per_step = float(m_pred.group(3))
-        value = 1000.0 / ms_per_step
-        eval_ms = sum(e[0] for e in evals)
-        base = 1000.0 / PUBLISHED_MS_PER_TOKEN.get(n, PUBLISHED_MS_PER_TOKEN[1])
-        finish({"metric": "decode tokens/sec (batch-1 sequence, greedy) + prefill TTFT, Llama-3.1-8B q40" if args.model == "llama-3.1-8b"
-                          else f"decode tokens/sec + prefill TTFT, {args.model} q40",
-                "value": round(value, 3), "unit": "tokens/s", "n_gpus": n, "steps": len(timed) or int(m_pred.group(1)), "warmup": warm,
-                "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / base, 2),
-                "dtype": "q40 weights, q80 activations (reference CPU build, AVX)", "data": "synthetic (same .m/.t files)",
-                "config": {"model": args.model, "global_batch": 1, "prompt_len": args.prompt_len, "parallelism": f"tp{n} (root + {n - 1} TCP-loopback workers)",
-                           "nthreads_per_node": threads, "note": "the reference has no CUDA path; its stock build runs on the host CPUs"},
-                "ttft_ms": eval_ms, "impl": "reference", "reference_summary_tokens_per_s": float(m_pred.group(2)), "wall_s": round(wall, 1)})
-    except subprocess.TimeoutExpired:
-        finish({"impl": "reference", "unavailable": "reference run timed out"})
-    finally:
-        for p in workers:
-            try:
-                p.kill()
-            except Exception:
-                pass
+    cpus, tpc = _cpu_topology()
+    phys_per_proc = max(1, len(cpus) // tpc // n)
+    cands = sorted({t for t in (4, 8, 16, 32, 64) if t <= phys_per_proc} | {1 << (max(1, min(64, phys_per_proc)).bit_length() - 1)})
+    warm = max(args.warmup, 3)
+    deadline = time.time() + args.ref_timeout
+    sweep = {}
+    best_t = cands[-1]
+    if len(cands) > 1:
+        for t in cands:
+            if time.time() > deadline - 0.6 * args.ref_timeout:
+                break
+            r = _run_reference_once(exe, args, model_path, tok_path, n, t, 8, 2, cpus, max(60, int(deadline - time.time())))
+            if "error" not in r:
+                sweep[t] = round(1000.0 / r["ms_per_step"], 3)
+        if sweep:
+            best_t = max(sweep, key=sweep.get)
+    r = _run_reference_once(exe, args, model_path, tok_path, n, best_t, args.steps, warm, cpus, max(60, int(deadline - time.time())))
+    if "error" in r:
+        return finish({"impl": "reference", "unavailable": r["error"]})
+    value = 1000.0 / r["ms_per_step"]
+    base = 1000.0 / PUBLISHED_MS_PER_TOKEN.get(n, PUBLISHED_MS_PER_TOKEN[1])
+    finish({"metric": "decode tokens/sec (batch-1 sequence, greedy) + prefill TTFT, Llama-3.1-8B q40" if args.model == "llama-3.1-8b"
+                      else f"decode tokens/sec + prefill TTFT, {args.model} q40",
+            "value": round(value, 3), "unit": "tokens/s", "n_gpus": n, "steps": r["n_timed"], "warmup": warm,
+            "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / base, 2),
+            "dtype": "q40 weights, q80 activations (reference CPU build, AVX)", "data": "synthetic (same .m/.t files)",
+            "config": {"model": args.model, "global_batch": 1, "seq_len": args.prompt_len + args.steps, "prompt_len": args.prompt_len,
+                       "parallelism": f"tp{n}", "launch": f"root + {n - 1} TCP-loopback workers, pinned to disjoint CPU sets",
+                       "nthreads_per_node": r["threads"], "nthreads_sweep_tok_s": sweep,
+                       "note": "the reference has no CUDA path; its stock build runs on the host CPUs"},
+            "ttft_ms": r["eval_ms"], "prefill_tokens_per_s": round(max(1, args.prompt_len - 1) / max(1e-3, r["eval_ms"]) * 1e3, 1),
+            # end to end = the reference's own root-side wall clock per generated token (forward + host sampling + printing)
+            "e2e": {"value": r["summary_tok_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "reference summary line `Prediction tokens/s` (root wall clock, CPU only: no device copies)"},
+            "gpu_launches": 0, "impl": "reference", "reference_summary_tokens_per_s": r["summary_tok_s"], "wall_s": round(r["wall"], 1)})
 
 
 def main():

@@ -26,6 +26,7 @@ struct Engine {
     int lastError = 0;
     uint64_t *trace = nullptr;   // device buffer [maxLaunches][4] of globaltimer stamps (optional)
     uint32_t traceCap = 0;
+    bool traceAllCtas = false;   // persistent kernel: every CTA records its phase stamps (skew analysis, tools/trace_mega.py --all)
     MegaLayer *megaLayers = nullptr;   // device copy of the per-layer pointer table for the persistent decode kernel
     unsigned int *megaCounter = nullptr;
     bool useMega = false;
@@ -102,6 +103,8 @@ static int engineDecodeMega(Engine &e, bool greedyAdvance, cudaStream_t stream) 
     m.argVal = e.g.argVal; m.argIdx = e.g.argIdx; m.argCounter = e.g.argCounter; m.gridCounter = e.megaCounter;
     m.rowOffsetGlobal = c.rank * c.vocab; m.greedyAdvance = greedyAdvance ? 1u : 0u;
     m.trace = e.trace;
+    m.traceCtas = e.traceAllCtas ? c.numSms : 1u;
+    m.traceStride = e.traceAllCtas ? (uint32_t)(((size_t)e.traceCap * 4) / c.numSms) : 0u;
     if (e.comm.nRanks > 1) fillAr(e, m.ar, 0);
     return launchMegaDecode(m, (int)c.numSms, stream);
 }
@@ -326,6 +329,11 @@ DL_EXPORT int dl_engine_set_comm(void *h, const dl::CommPtrs *p) {
 DL_EXPORT int dl_engine_set_trace(void *h, uint64_t *buf, uint32_t capLaunches) {
     ((Engine *)h)->trace = buf;
     ((Engine *)h)->traceCap = capLaunches;
+    return 0;
+}
+
+DL_EXPORT int dl_engine_set_trace_all(void *h, int allCtas) {
+    ((Engine *)h)->traceAllCtas = allCtas != 0;
     return 0;
 }
 

@@ -152,6 +152,7 @@ struct MegaArgs {
     uint32_t rowOffsetGlobal;
     uint32_t greedyAdvance;      // 1: publish the arg-max token and advance the position on the device
     uint64_t *trace;
+    uint32_t traceCtas, traceStride;   // CTAs 0..traceCtas-1 record their phase stamps at trace[cta * traceStride + slot]
     ArArgs ar;
 };
 

@@ -67,7 +67,7 @@ __device__ __forceinline__ void megaTile(const MegaPhase &P, uint32_t &pairBegin
 template <int PRO, int EPI>
 __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase &P, const float *in, const float *normW, float *out,
                          uint32_t arParity, RingPos &ring, int tid, uint32_t &slot) {
-    auto stamp = [&]() { if (m.trace && blockIdx.x == 0 && tid == 0) m.trace[slot] = globalTimerNs(); slot++; };
+    auto stamp = [&]() { if (m.trace && tid == 0 && blockIdx.x < m.traceCtas) m.trace[(size_t)blockIdx.x * m.traceStride + slot] = globalTimerNs(); slot++; };
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t n = P.n;
     const uint32_t nblk = P.nblk, nseg = P.nseg;
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_
     unsigned int barTarget = 0;
     RingPos ring{0u, 0u};
     uint32_t slot = 0;
-    auto stamp = [&]() { if (m.trace && blockIdx.x == 0 && tid == 0) m.trace[slot] = globalTimerNs(); slot++; };
+    auto stamp = [&]() { if (m.trace && tid == 0 && blockIdx.x < m.traceCtas) m.trace[(size_t)blockIdx.x * m.traceStride + slot] = globalTimerNs(); slot++; };
     stamp();
     // embedding: CTA c copies its slice of the row
     {

@@ -76,8 +76,26 @@ def lib() -> C.CDLL:
                        ("dl_comm_ipc_open", [vp, C.POINTER(vp)]), ("dl_comm_ipc_close", [vp]), ("dl_comm_memset", [vp, i32, C.c_size_t, vp])):
         getattr(L, name).argtypes = args
         getattr(L, name).restype = i32
+    L.dl_vmm_supported.argtypes = [C.POINTER(C.c_int)]
+    L.dl_vmm_supported.restype = i32
+    L.dl_vmm_create.argtypes = [u32, u32, C.c_size_t, C.c_char_p, i32]
+    L.dl_vmm_create.restype = vp
+    L.dl_vmm_connect.argtypes = [vp]
+    L.dl_vmm_connect.restype = i32
+    L.dl_vmm_ptr.argtypes = [vp, u32]
+    L.dl_vmm_ptr.restype = vp
+    L.dl_vmm_mc_ptr.argtypes = [vp]
+    L.dl_vmm_mc_ptr.restype = vp
+    L.dl_vmm_bytes.argtypes = [vp]
+    L.dl_vmm_bytes.restype = C.c_size_t
+    L.dl_vmm_destroy.argtypes = [vp]
+    L.dl_vmm_destroy.restype = None
+    L.dl_vmm_selftest_kernel.argtypes = [vp, u32, i32, vp]
+    L.dl_vmm_selftest_kernel.restype = i32
     L.dl_engine_set_trace.argtypes = [vp, vp, u32]
     L.dl_engine_set_trace.restype = i32
+    L.dl_engine_set_trace_all.argtypes = [vp, i32]
+    L.dl_engine_set_trace_all.restype = i32
     L.dl_engine_num_sms.argtypes = [vp]
     L.dl_engine_num_sms.restype = u32
     L.dl_engine_forward.argtypes = [vp, i32, i32, i32, vp]

@@ -56,8 +56,11 @@ class Communicator:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self._lib = cl.lib()
         self.arena_ptrs: List[int] = []
+        self.mc_ptr: int = 0             # NVLS multicast mapping of the arena (0: not available, kernels use unicast peer stores)
+        self.arena_kind = "none"         # "vmm" (cuMem* + multicast) or "ipc" (cudaMalloc + CUDA IPC)
         self.layout: ArenaLayout | None = None
         self._local = None
+        self._vmm = None
         # Peer-memory (CUDA IPC over NVLink) collectives need every rank on one host; otherwise the engine falls back to NCCL.
         import socket
         hosts = [None] * self.world_size
@@ -68,8 +71,58 @@ class Communicator:
     def is_root(self) -> bool:
         return self.rank == 0
 
+    _arena_seq = 0
+
     def alloc_arena(self, layout: ArenaLayout) -> None:
+        """Creates the symmetric arena. Preferred: CUDA VMM allocation shared through POSIX descriptors with an NVLS multicast
+        mapping (csrc/cuda/comm_vmm.cu); fallback: cudaMalloc + CUDA IPC handles (no multicast)."""
+        import os
         self.layout = layout
+        if os.environ.get("DL_NO_VMM") is None and self._alloc_vmm(layout):
+            return
+        self._alloc_ipc(layout)
+
+    def _alloc_vmm(self, layout: ArenaLayout) -> bool:
+        import os
+        lib = self._lib
+        flags = C.c_int(0)
+        if lib.dl_vmm_supported(C.byref(flags)) != 0:
+            flags.value = 0
+        ok = torch.tensor([1 if (flags.value & 1) else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            return False
+        Communicator._arena_seq += 1
+        nonce = [None]
+        if self.rank == 0:
+            nonce[0] = f"{os.getpid()}-{Communicator._arena_seq}-{int.from_bytes(os.urandom(4), 'little')}"
+        dist.broadcast_object_list(nonce, src=0)
+        want_mc = 0 if os.environ.get("DL_NO_MULTICAST") is not None else 1
+        h = lib.dl_vmm_create(self.rank, self.world_size, layout.total, nonce[0].encode(), want_mc)
+        ok = torch.tensor([1 if h else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if h:
+                lib.dl_vmm_destroy(h)
+            return False
+        rc = lib.dl_vmm_connect(h)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            raise RuntimeError(f"rank {self.rank}: VMM arena bootstrap failed (code {rc}); set DL_NO_VMM=1 to use the CUDA IPC arena")
+        self._vmm = h
+        self.arena_ptrs = [int(lib.dl_vmm_ptr(h, r)) for r in range(self.world_size)]
+        self._local = self.arena_ptrs[self.rank]
+        mc = lib.dl_vmm_mc_ptr(h)
+        # the multicast mapping is used only if every rank has it
+        have = torch.tensor([1 if mc else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(have, op=dist.ReduceOp.MIN)
+        self.mc_ptr = int(mc) if (mc and int(have.item()) == 1) else 0
+        self.arena_kind = "vmm"
+        dist.barrier()
+        return True
+
+    def _alloc_ipc(self, layout: ArenaLayout) -> None:
         ptr = C.c_void_p()
         cl.check(self._lib.dl_comm_alloc(layout.total, C.byref(ptr)), "comm_alloc")
         self._local = ptr.value
@@ -87,6 +140,8 @@ class Communicator:
                 out = C.c_void_p()
                 cl.check(self._lib.dl_comm_ipc_open(buf, C.byref(out)), "comm_ipc_open")
                 self.arena_ptrs.append(out.value)
+        self.mc_ptr = 0
+        self.arena_kind = "ipc"
         dist.barrier()
 
     def comm_ptrs(self, slot_stride: int) -> cl.CommPtrs:

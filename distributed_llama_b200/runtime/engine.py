@@ -149,11 +149,16 @@ class Engine:
         self._graph_ready = False
 
     # -- tracing --
-    def enable_trace(self, cap_launches: int = 1024):
+    def enable_trace(self, cap_launches: int = 1024, all_ctas: bool = False):
         """Device-side timeline: every kernel stamps globaltimer at entry / dependency resolved / prologue done / exit.
-        Must be enabled before the decode graph is captured."""
+        Must be enabled before the decode graph is captured. `all_ctas`: every CTA of the persistent kernel records its own
+        phase stamps (row c of `trace_buf.view(num_sms, -1)`), for barrier-skew analysis."""
+        if all_ctas:
+            cap_launches = max(cap_launches, self.num_sms * 256)
         self.trace_buf = torch.zeros(cap_launches, 4, dtype=torch.int64, device=self.device)
         cl.check(self._lib.dl_engine_set_trace(self._h, self.trace_buf.data_ptr(), cap_launches), "engine_set_trace")
+        cl.check(self._lib.dl_engine_set_trace_all(self._h, 1 if all_ctas else 0), "engine_set_trace_all")
+        self.trace_stride = (cap_launches * 4) // self.num_sms if all_ctas else 0
         self._graph_ready = False
 
     def read_trace(self):
