@@ -159,11 +159,12 @@ int maxLen(const std::vector<std::string> &v) {
 }  // namespace
 
 ApiServer::ApiServer(InferenceBackend &backend, Tokenizer &tokenizer, const ApiConfig &cfg)
-    : backend_(backend), tok_(tokenizer), cfg_(cfg), sampler_(backend.vocabSize(), cfg.temperature, cfg.topp, cfg.seed),
+    : backend_(backend), tok_(tokenizer), cfg_(cfg), sampler_(std::min<uint32_t>(backend.vocabSize(), tokenizer.vocabSize()), cfg.temperature, cfg.topp, cfg.seed),
       stops_(stopPieces(tokenizer)),
       gen_(cfg.chatTemplate.empty() ? TEMPLATE_UNKNOWN : parseChatTemplateType(cfg.chatTemplate), tokenizer.data().chatTemplate,
            stops_.empty() ? std::string() : stops_[0]),
       det_(tokenizer.data().eosIds, stops_, maxLen(stops_), maxLen(stops_)) {
+    backend_.setVocabLimit(tokenizer.vocabSize());
     std::printf("⭐ Chat template: %s\n", chatTemplateTypeName(gen_.type()));
     for (const std::string &s : stops_) std::printf("🛑 Stop: %s\n", s.c_str());
 }

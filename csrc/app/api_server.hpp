@@ -17,6 +17,7 @@ struct InferenceBackend {
     virtual ~InferenceBackend() {}
     virtual uint32_t seqLen() const = 0;
     virtual uint32_t vocabSize() const = 0;
+    virtual void setVocabLimit(uint32_t) {}   // greedy decoding never returns ids >= limit (tokenizer vocabulary)
     virtual void prefill(const std::vector<int32_t> &tokens, uint32_t pos) = 0;
     virtual int32_t next(int32_t token, uint32_t pos, Sampler &sampler) = 0;   // greedy on the device when temperature == 0
 };

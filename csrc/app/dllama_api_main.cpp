@@ -21,6 +21,7 @@ struct EngineBackend : InferenceBackend {
     explicit EngineBackend(NativeEngine &engine) : e(engine), tmp(engine.header().vocabSize) {}
     uint32_t seqLen() const override { return e.seqLen(); }
     uint32_t vocabSize() const override { return e.header().vocabSize; }
+    void setVocabLimit(uint32_t limit) override { e.setVocabLimit(limit); }
     void prefill(const std::vector<int32_t> &tokens, uint32_t pos) override { if (!tokens.empty()) e.prefill(tokens, pos); }
     int32_t next(int32_t token, uint32_t pos, Sampler &sampler) override {
         if (sampler.temperature() == 0.f) return e.stepGreedy(token, pos);

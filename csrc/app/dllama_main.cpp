@@ -80,12 +80,15 @@ struct App {
     Sampler sampler;
     App(const Args &a)
         : args(a), engine(a.model, a.maxSeqLen, a.gpuIndex), tokenizer(a.tokenizer),
-          sampler(engine.header().vocabSize, a.temperature, a.topp, a.seed) {}
+          sampler(std::min<uint32_t>(tokenizer.vocabSize(), engine.header().vocabSize), a.temperature, a.topp, a.seed) {
+        // sampling ranges over the tokenizer's vocabulary (reference src/app.cpp:243-246); padded embedding rows never win
+        engine.setVocabLimit(tokenizer.vocabSize());
+    }
 
     int32_t next(int32_t token, uint32_t pos) {
         if (sampler.temperature() == 0.f) return engine.stepGreedy(token, pos);
         const float *logits = engine.step(token, pos);
-        std::vector<float> tmp(logits, logits + engine.header().vocabSize);
+        std::vector<float> tmp(logits, logits + std::min<uint32_t>(tokenizer.vocabSize(), engine.header().vocabSize));
         return sampler.sample(tmp.data());
     }
 };

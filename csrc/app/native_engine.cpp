@@ -136,6 +136,7 @@ NativeEngine::NativeEngine(const std::string &modelPath, uint32_t maxSeqLen, int
         cfg.vocab = vocab; cfg.seqLen = seqLen_; cfg.nExperts = h_.nExperts; cfg.nActiveExperts = h_.nActiveExperts; cfg.maxBatch = mb;
         cfg.nSplits = nSplits_; cfg.rank = 0; cfg.nRanks = 1; cfg.numSms = (uint32_t)sms; cfg.eps = h_.normEpsilon; cfg.usePdl = 1;
         cfg.moeFirstExpert = 0; cfg.moeNumLocal = h_.nExperts; cfg.wType = 0;
+        cfg.hiddenAct = h_.hiddenAct == ACT_GELU ? 1u : 0u;
         I.engine = dl_engine_create(&cfg);
         if (!I.engine) throw std::runtime_error("dl_engine_create failed");
         for (uint32_t l = 0; l < h_.nLayers; l++) {
@@ -339,5 +340,11 @@ int32_t NativeEngine::stepGreedy(int32_t token, uint32_t pos) {
 }
 
 void NativeEngine::synchronize() { cudaCheck(cudaStreamSynchronize(impl_->stream), "synchronize"); }
+
+void NativeEngine::setVocabLimit(uint32_t limit) {
+    if (limit >= h_.vocabSize) limit = 0;
+    engCheck(dl_engine_set_vocab_limit(impl_->engine, limit), "dl_engine_set_vocab_limit");
+    graphReady_ = false;   // the limit is a launch parameter of the captured step
+}
 
 }  // namespace dl

@@ -123,5 +123,12 @@ __device__ __forceinline__ void traceStamp(uint64_t *trace, int which) {
 }
 
 __device__ __forceinline__ float siluf(float x) { return x / (1.0f + __expf(-x)); }
+// Gate activation of the feed-forward block, selected by the `.m` header's hidden_act (reference OP_SILU / OP_GELU,
+// src/nn/nn-cpu-ops.cpp:454-500; gelu = tanh approximation). act: 0 = SiLU, 1 = GELU.
+__device__ __forceinline__ float gateAct(float x, uint32_t act) {
+    if (act == 0u) return siluf(x);
+    const float u = 0.7978845608028654f * x * (1.0f + 0.044715f * x * x);
+    return 0.5f * x * (1.0f + tanhf(u));
+}
 
 }  // namespace dl

@@ -14,6 +14,8 @@
 
 namespace dl {
 
+uint32_t gHiddenAct = 0;
+
 static_assert(kApiMaxRanks == kMaxRanks, "engine_api.h and kernels.h disagree on the rank limit");
 
 struct Engine {
@@ -30,6 +32,7 @@ struct Engine {
     MegaLayer *megaLayers = nullptr;   // device copy of the per-layer pointer table for the persistent decode kernel
     unsigned int *megaCounter = nullptr;
     bool useMega = false;
+    uint32_t vocabLimit = 0;     // 0 = none; otherwise the greedy arg-max ignores vocabulary rows >= vocabLimit
     bool fusedAttn = true, fusedArgmax = true, useTma = true;   // debugging switches (DL_NO_FUSED_ATTN / DL_NO_FUSED_ARGMAX / DL_NO_TMA)
 };
 
@@ -47,6 +50,10 @@ static void fillAr(const Engine &e, ArArgs &ar, uint32_t parity) {
         ar.slots[r] = (uint64_t *)(base + c.slotsOff);
         ar.cand[r] = (uint64_t *)(base + c.candValOff);
     }
+}
+
+static uint32_t localVocabLimit(const Engine &e) {
+    return (e.vocabLimit && e.vocabLimit < e.cfg.vocab) ? e.vocabLimit : e.cfg.vocab;
 }
 
 static int gemvSel(const Engine &e, int pro, int epi, int nb, const GemvArgs &a, int numSms, cudaStream_t stream, bool pdl) {
@@ -101,7 +108,7 @@ static int engineDecodeMega(Engine &e, bool greedyAdvance, cudaStream_t stream) 
     m.x = e.g.x; m.qkv = e.g.qkv; m.z = e.g.z; m.h = e.g.h; m.logits = e.g.logits;
     m.attnPartial = e.g.attnPartial; m.attnCounters = e.g.attnCounters;
     m.argVal = e.g.argVal; m.argIdx = e.g.argIdx; m.argCounter = e.g.argCounter; m.gridCounter = e.megaCounter;
-    m.rowOffsetGlobal = c.rank * c.vocab; m.greedyAdvance = greedyAdvance ? 1u : 0u;
+    m.rowOffsetGlobal = c.rank * c.vocab; m.greedyAdvance = greedyAdvance ? 1u : 0u; m.vocabLimit = e.vocabLimit;
     m.trace = e.trace;
     m.traceCtas = e.traceAllCtas ? c.numSms : 1u;
     m.traceStride = e.traceAllCtas ? (uint32_t)(((size_t)e.traceCap * 4) / c.numSms) : 0u;
@@ -189,21 +196,28 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
                 // logits + greedy sampling + position advance in one launch
                 a.argVal = e.g.argVal; a.argIdx = e.g.argIdx; a.argCounter = e.g.argCounter;
                 a.tokenOut = e.g.tokens; a.posInOut = e.g.pos; a.history = e.g.history; a.historyCap = c.seqLen;
-                a.rowOffsetGlobal = c.rank * c.vocab;
+                a.rowOffsetGlobal = c.rank * c.vocab; a.vocabLimit = e.vocabLimit;
                 if (e.comm.nRanks > 1) fillAr(e, a.ar, 0);
                 r = gemvQ40Tma(PRO_RMSNORM_, EPI_ARGMAX_, 1, a, c.numSms, stream, pdl);
                 if (r < 0) return r;
             }
             if (r == 1) {
+                // the stand-alone arg-max kernel sees this rank's vocabulary slice only: under tensor parallelism the ranks would
+                // pick different (local) ids, so the non-fused route is refused there instead of silently diverging
+                if (greedyAdvance && e.comm.nRanks > 1) return -33;
+                a.argVal = nullptr; a.argIdx = nullptr; a.argCounter = nullptr; a.tokenOut = nullptr; a.posInOut = nullptr; a.history = nullptr;
+                a.ar = ArArgs{};
                 DL_TRY(gemvSel(e, PRO_RMSNORM_, EPI_STORE_, 1, a, c.numSms, stream, pdl));
                 if (greedyAdvance)
-                    DL_TRY(launchArgmaxAdvance(e.g.logits, c.vocab, e.g.tokens, e.g.pos, e.g.history, c.seqLen, stream, pdl));
+                    DL_TRY(launchArgmaxAdvance(e.g.logits, localVocabLimit(e), e.g.tokens, e.g.pos, e.g.history, c.seqLen, stream, pdl));
             }
         } else {
             a.in = e.g.x;
             DL_TRY(gemvSel(e, PRO_RMSNORM_, EPI_STORE_, nb, a, c.numSms, stream, pdl));
-            if (greedyAdvance)
-                DL_TRY(launchArgmaxAdvance(e.g.logits, c.vocab, e.g.tokens, e.g.pos, e.g.history, c.seqLen, stream, pdl));
+            if (greedyAdvance) {
+                if (e.comm.nRanks > 1) return -33;
+                DL_TRY(launchArgmaxAdvance(e.g.logits, localVocabLimit(e), e.g.tokens, e.g.pos, e.g.history, c.seqLen, stream, pdl));
+            }
         }
     }
     return 0;
@@ -264,6 +278,7 @@ using dl::Engine;
 DL_EXPORT void *dl_engine_create(const dl::EngineConfig *cfg) {
     Engine *e = new Engine();
     e->cfg = *cfg;
+    dl::gHiddenAct = cfg->hiddenAct;
     e->layers.resize(cfg->nLayers);
     e->fusedAttn = std::getenv("DL_NO_FUSED_ATTN") == nullptr;
     e->fusedArgmax = std::getenv("DL_NO_FUSED_ARGMAX") == nullptr;
@@ -318,6 +333,13 @@ DL_EXPORT int dl_engine_enable_mega(void *h, int enable) {
         DL_CUDA_CHECK(cudaMemset(e->megaCounter, 0, 256));
     }
     e->useMega = enable != 0;
+    return 0;
+}
+
+DL_EXPORT int dl_engine_set_vocab_limit(void *h, uint32_t limit) {
+    Engine *e = (Engine *)h;
+    if (e->vocabLimit != limit && e->decodeGraph) { cudaGraphExecDestroy(e->decodeGraph); e->decodeGraph = nullptr; }   // the limit is baked into the captured launch
+    e->vocabLimit = limit;
     return 0;
 }
 

@@ -19,6 +19,7 @@ struct EngineConfig {   // mirrored by ctypes in distributed_llama_b200/ops/cuda
     uint32_t usePdl;
     uint32_t moeFirstExpert, moeNumLocal;   // experts held by this rank (expert parallelism); TP mode: 0, nExperts
     uint32_t wType;          // matrix storage: 0 = q40 device layout, 1 = dense f32, 2 = dense f16 (gemv_dense.cu)
+    uint32_t hiddenAct;      // gate activation: 0 = SiLU, 1 = GELU (tanh form) — the `.m` header's hidden_act
 };
 
 struct LayerPtrs {
@@ -80,6 +81,7 @@ int dl_engine_set_layer(void *h, uint32_t layer, const dl::LayerPtrs *p);
 int dl_engine_set_globals(void *h, const dl::GlobalPtrs *p);
 int dl_engine_set_comm(void *h, const dl::CommPtrs *p);
 int dl_engine_enable_mega(void *h, int enable);
+int dl_engine_set_vocab_limit(void *h, uint32_t limit);   // greedy arg-max never returns ids >= limit (tokenizer vocabulary size)
 int dl_engine_set_trace(void *h, uint64_t *buf, uint32_t capLaunches);
 int dl_engine_set_trace_all(void *h, int allCtas);
 uint32_t dl_engine_num_sms(void *h);

@@ -44,6 +44,7 @@ struct GemmArgs {
     ArArgs ar;             // GEPI_RESIDUAL_AR: tensor-parallel all-reduce fused into the epilogue (LL words over peer memory)
     uint32_t rawStages;    // TMA-staged variant: depth of the raw q40 ring (2 or 3)
     uint32_t debugFlags;   // bit0: skip the proxy fence, bit1: skip the A-tile stores (timing experiments only)
+    uint32_t act;          // gate activation of GEPI_SWIGLU_BF16 (gHiddenAct)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcKernel(const __grid_co
                     if (EPI == GEPI_SWIGLU_BF16) {
                         const float other = __shfl_xor_sync(0xffffffffu, v, 1);   // rows (2i, 2i+1) = (gate_i, up_i)
                         if (tok < a.T && fOk && !(lane & 1))
-                            reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(siluf(v) * other);
+                            reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(gateAct(v, a.act) * other);
                     } else if (tok < a.T && fOk) {
                         if (EPI == GEPI_STORE_F32) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v;
                         if (EPI == GEPI_RESIDUAL) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v + resid[j];
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                         if (EPI == GEPI_SWIGLU_BF16) {
                             const float other = __shfl_xor_sync(0xffffffffu, v, 1);
                             if (fOk && tok < a.T && !(lane & 1))
-                                reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(siluf(v) * other);
+                                reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(gateAct(v, a.act) * other);
                         } else if (fOk && tok < a.T) {
                             if (EPI == GEPI_STORE_F32) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v;
                             if (EPI == GEPI_RESIDUAL) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = res[j] + v;
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                     if (EPI == GEPI_SWIGLU_BF16) {
                         const float other = __shfl_xor_sync(0xffffffffu, v, 1);
                         if (tok < a.T && fOk && !(lane & 1))
-                            reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(siluf(v) * other);
+                            reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(gateAct(v, a.act) * other);
                     } else if (tok < a.T && fOk) {
                         if (EPI == GEPI_STORE_F32) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v;
                         if (EPI == GEPI_RESIDUAL) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v + resid[j];
@@ -688,6 +689,7 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
     bool tma = variant == 2 || (variant == 0 && n % 256 == 0);
     if (tma && n % 256) return -6;
     GemmArgs a{};
+    a.act = gHiddenAct;
     a.qs = (const uint32_t *)qs; a.scales = (const __half *)scales; a.d = d; a.n = n; a.T = T;
     a.nTile = (T + 15) / 16 * 16;
     a.out = out; a.outStride = outStride;

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) gemvDenseKernel(GemvArgs a) 
         for (uint32_t i = tid; i < tilePairs * NB; i += kDenseThreads) {
             const uint32_t p = i / NB, t = i - p * NB;
             const float g = rowOut[(size_t)(2 * p) * NB + t], up = rowOut[(size_t)(2 * p + 1) * NB + t];
-            a.out[(size_t)t * a.outStride + pairBegin + p] = siluf(g) * up;
+            a.out[(size_t)t * a.outStride + pairBegin + p] = gateAct(g, a.act) * up;
         }
     } else {
         for (uint32_t i = tid; i < tileRows * NB; i += kDenseThreads) {
@@ -202,6 +202,7 @@ size_t gemvDenseSmemBytes(uint32_t n, uint32_t maxTileRows, int nb) {
 // wtype: 1 = f32, 2 = f16. `a.qs` points at the row-major [d][n] matrix, `a.scales` is unused.
 int gemvDense(int wtype, int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl) {
     if (a.d % 2 || a.n % 8) return -1;
+    a.act = gHiddenAct;
     if (a.expertIdx || a.moeCtasPerSlot || a.ar.nRanks > 1) return -40;   // MoE routing / in-kernel all-reduce: q40 kernels only
     const uint32_t nPairs = a.d / 2;
     const int grid = (int)(nPairs < (uint32_t)numSms ? nPairs : (uint32_t)numSms);

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemvQ40Kernel(GemvArgs a) {
                 g += partial[((size_t)(2 * p) * nseg + sg) * NB + t];
                 up += partial[((size_t)(2 * p + 1) * nseg + sg) * NB + t];
             }
-            a.out[(size_t)t * a.outStride + pairBegin + p] = siluf(g) * up;
+            a.out[(size_t)t * a.outStride + pairBegin + p] = gateAct(g, a.act) * up;
         }
     } else {
         for (uint32_t i = tid; i < tileRows * NB; i += kGemvThreads) {
@@ -258,6 +258,7 @@ static int launchGemv(const GemvArgs &a, int grid, size_t smemBytes, cudaStream_
 
 int gemvQ40(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl) {
     if (a.d % 2 || a.n % 32 || (a.n / 4) % 8) return -1;
+    a.act = gHiddenAct;
     const uint32_t nPairs = a.d / 2;
     const int grid = (int)(nPairs < (uint32_t)numSms ? nPairs : (uint32_t)numSms);
     a.maxTileRows = 2 * ((nPairs + grid - 1) / grid);

@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
         float *outBase = a.out + (size_t)slot * a.outSlotStride;
         for (uint32_t i = tid; i < tilePairs * NB; i += kConsumerThreads) {
             const uint32_t p = i / NB, t = i - p * NB;
-            outBase[(size_t)t * a.outStride + pairBegin + p] = active ? siluf(rowSum(2 * p, t)) * rowSum(2 * p + 1, t) : 0.f;
+            outBase[(size_t)t * a.outStride + pairBegin + p] = active ? gateAct(rowSum(2 * p, t), a.act) * rowSum(2 * p + 1, t) : 0.f;
         }
     } else if (EPI == EPI_RESIDUAL || EPI == EPI_MOE_DOWN) {
         __shared__ bool sLastSlot;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kTmaThreads, (NB == 1 ? 2 : 1)) gemvQ40TmaKern
             const uint32_t r = i / NB, t = i - r * NB;
             const float v = rowSum(r, t);
             a.out[(size_t)t * a.outStride + rowBase + r] = v;
-            if (EPI == EPI_ARGMAX && v > best) { best = v; bestIdx = (int)(a.rowOffsetGlobal + rowBase + r); }   // rows ascend per thread
+            if (EPI == EPI_ARGMAX && v > best && a.rowOffsetGlobal + rowBase + r < a.vocabLimit) { best = v; bestIdx = (int)(a.rowOffsetGlobal + rowBase + r); }   // rows ascend per thread
         }
         if (EPI == EPI_ARGMAX) {
             // greedy sampling fused into the logits kernel: CTA-level arg-max, then the last CTA to finish reduces
@@ -444,6 +444,8 @@ static int launchTma(const GemvArgs &a, const TmaGemvGeom &geo, int grid, size_t
 // Returns 1 when the shape cannot use the TMA path (caller falls back), <0 on errors, 0 on success.
 int gemvQ40Tma(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl) {
     if (a.d % 2 || a.n % 128) return 1;   // bulk copies need 16-byte aligned row starts for the fp16 scale rows
+    a.act = gHiddenAct;
+    if (a.vocabLimit == 0) a.vocabLimit = 0xffffffffu;
     const uint32_t nblk = a.n / 32, nseg = (nblk + 31) / 32;
     const uint32_t nPairs = a.d / 2;
     int grid = (int)(nPairs < (uint32_t)numSms ? nPairs : (uint32_t)numSms);

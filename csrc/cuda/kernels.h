@@ -9,6 +9,8 @@ enum { EPI_STORE_ = 0, EPI_RESIDUAL_ = 1, EPI_SWIGLU_ = 2, EPI_ARGMAX_ = 3, EPI_
 
 // In-kernel one-shot all-reduce over NVLink peer memory (see the EPI_RESIDUAL epilogue of gemv_q40_tma.cu).
 constexpr int kMaxRanks = 8;
+extern uint32_t gHiddenAct;   // process-wide gate activation (0 = SiLU, 1 = GELU), set by dl_engine_create from the model header
+
 struct ArArgs {
     uint32_t nRanks, rank, parity, maxCtas;
     uint32_t slotStride;          // words per (parity, source rank) slot = maxBatch * dim
@@ -46,6 +48,8 @@ struct GemvArgs {
     float *moeScratch;          // [kActive][d] weighted per-slot products (EPI_MOE_DOWN)
     unsigned int *moeCounters;  // [moeCtasPerSlot], zero-initialised, self-resetting
     ArArgs ar;                // ar.nRanks > 1: EPI_RESIDUAL sums the partial products of all ranks before the residual add
+    uint32_t act;             // gate activation of EPI_SWIGLU (filled in by the launchers from gHiddenAct)
+    uint32_t vocabLimit;      // EPI_ARGMAX: rows (global index) >= vocabLimit never win (model vocabulary padded beyond the tokenizer's); 0 = no limit
 };
 int gemvQ40(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl);      // per-thread loads (fallback)
 int gemvQ40Tma(int pro, int epi, int nb, GemvArgs a, int numSms, cudaStream_t stream, bool pdl);   // TMA ring; returns 1 if shape unsupported
@@ -117,7 +121,7 @@ int launchMoeRouter(const RouterArgs &a, int nb, cudaStream_t stream, bool pdl);
 int launchEmbedding(const float *table, const int *tokens, float *x, uint32_t dim, uint32_t xStride, uint32_t vocab, int nb,
                     cudaStream_t stream);
 int launchArgmaxAdvance(const float *logits, uint32_t vocab, int *tokenOut, int *pos, int *history, uint32_t historyCap,
-                        cudaStream_t stream, bool pdl);
+                        cudaStream_t stream, bool pdl);   // single rank only: the index is local to `logits`
 
 // Persistent decode kernel (mega_decode.cu)
 struct MegaLayer {
@@ -151,6 +155,7 @@ struct MegaArgs {
     MegaPhase ph[5];
     uint32_t rowOffsetGlobal;
     uint32_t greedyAdvance;      // 1: publish the arg-max token and advance the position on the device
+    uint32_t act, vocabLimit;    // see GemvArgs
     uint64_t *trace;
     uint32_t traceCtas, traceStride;   // CTAs 0..traceCtas-1 record their phase stamps at trace[cta * traceStride + slot]
     ArArgs ar;

@@ -231,7 +231,7 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
         return v;
     };
     if (EPI == EPI_SWIGLU_) {
-        for (uint32_t p = tid; p < tileRows / 2; p += kConsumerThreads) out[pairBegin + p] = siluf(rowSum(2 * p)) * rowSum(2 * p + 1);
+        for (uint32_t p = tid; p < tileRows / 2; p += kConsumerThreads) out[pairBegin + p] = gateAct(rowSum(2 * p), m.act) * rowSum(2 * p + 1);
     } else if (EPI == EPI_RESIDUAL_) {
         if (m.ar.nRanks > 1) {
             const ArArgs &ar = m.ar;
@@ -262,7 +262,7 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
         for (uint32_t r = tid; r < tileRows; r += kConsumerThreads) {
             const float v = rowSum(r);
             out[rowBase + r] = v;
-            if (EPI == EPI_ARGMAX_ && v > best) { best = v; bestIdx = (int)(m.rowOffsetGlobal + rowBase + r); }
+            if (EPI == EPI_ARGMAX_ && v > best && m.rowOffsetGlobal + rowBase + r < m.vocabLimit) { best = v; bestIdx = (int)(m.rowOffsetGlobal + rowBase + r); }
         }
         if (EPI == EPI_ARGMAX_) {
             auto better = [](float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); };
@@ -658,6 +658,8 @@ int launchMegaDecode(MegaArgs m, int numSms, cudaStream_t stream) {
     }
     if (maxN > 8 * kConsumerThreads * 4 || m.dim > 4 * kConsumerThreads * 4) return 1;   // activation (+ norm) vectors live in registers during the prologue
     const uint32_t grid = (uint32_t)numSms;
+    m.act = gHiddenAct;
+    if (m.vocabLimit == 0) m.vocabLimit = 0xffffffffu;
     // partial buffer: rows of the largest tile x segments; also hosts the attention scratch (16 x HD + 32 floats)
     const uint32_t ds[5] = {qDim + 2 * m.nKvHeads * m.headDim, m.dim, 2 * m.ffDim, m.dim, m.vocab};
     const uint32_t dn[5] = {m.dim, qDim, m.dim, m.ffDim, m.dim};

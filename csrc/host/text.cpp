@@ -42,6 +42,7 @@ TokenizerData readTokenizerFile(const std::string &path) {
         const int32_t headerSize = readPod<int32_t>(f, "header size");
         if (headerSize < 8 || (headerSize - 8) % 8) throw std::runtime_error("Invalid tokenizer header size");
         int32_t version = -1, templateLen = -1, nEos = 0;
+        int64_t chatStopSkip = 0;   // legacy key: bytes of an (ignored) stop string stored right after the header
         for (int i = 0; i < (headerSize - 8) / 8; i++) {
             const int32_t key = readPod<int32_t>(f, "header key");
             const int32_t value = readPod<int32_t>(f, "header value");
@@ -52,7 +53,7 @@ TokenizerData readTokenizerFile(const std::string &path) {
                 case TK_BOS_ID: d.bosId = value; break;
                 case TK_EOS_ID: case TK_CHAT_EOS_ID: d.eosIds.push_back(value); break;  // legacy keys
                 case TK_CHAT_TEMPLATE: templateLen = value; break;
-                case TK_CHAT_STOP: f.seekg(value, std::ios::cur); break;
+                case TK_CHAT_STOP: chatStopSkip += value; break;   // applied after the whole header has been read (reference src/tokenizer.cpp:68-86)
                 case TK_PAD_ID: break;
                 case TK_N_EOS_TOKENS: nEos = value; break;
                 case TK_ADD_BOS: d.addBos = value == 1; break;
@@ -60,6 +61,7 @@ TokenizerData readTokenizerFile(const std::string &path) {
             }
         }
         if (version != 1) throw std::runtime_error("Old tokenizer version, please regenerate your tokenizer");
+        if (chatStopSkip > 0) f.seekg(chatStopSkip, std::ios::cur);
         if (templateLen > 0) {
             d.chatTemplate.resize(templateLen);
             f.read(&d.chatTemplate[0], templateLen);

@@ -49,6 +49,8 @@ class InferenceSession:
         self.tokenizer = H.Tokenizer(tokenizer_path) if tokenizer_path else None
         vocab = self.tokenizer.vocab_size if self.tokenizer else self.header.vocab_size
         self.sampler = H.Sampler(vocab, temperature, topp, seed)
+        if self.tokenizer and self.tokenizer.vocab_size < self.header.vocab_size:
+            self.engine.set_vocab_limit(self.tokenizer.vocab_size)
         self.pos = 0
         self._pin_in = torch.zeros(2, dtype=torch.int32).pin_memory()
         self._pin_out = torch.zeros(1, dtype=torch.int32).pin_memory()

@@ -132,7 +132,7 @@ def run_inference_app(args: AppArgs, handler: Callable[[AppContext], None]) -> N
     if header.weight_type == H.F_Q40 and args.buffer_float_type != "q80":
         raise RuntimeError("This version supports only Q40 weights with Q80 sync type")
     sess = InferenceSession(args.model, args.tokenizer, max_seq_len=args.max_seq_len, temperature=args.temperature,
-                            topp=args.topp, seed=args.seed, comm=comm)
+                            topp=args.topp, seed=args.seed, comm=comm, moe_mode=getattr(args, "moe_mode", "auto") or "auto")
     if rank != 0:
         worker_loop(sess, comm)
         return

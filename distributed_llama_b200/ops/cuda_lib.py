@@ -18,7 +18,7 @@ u32, u64, i32, f32, vp = C.c_uint32, C.c_uint64, C.c_int, C.c_float, C.c_void_p
 class EngineConfig(C.Structure):
     _fields_ = [(n, u32) for n in ("dim", "nLayers", "nHeads", "nKvHeads", "headDim", "ffDim", "vocab", "seqLen",
                                    "nExperts", "nActiveExperts", "maxBatch", "nSplits", "rank", "nRanks", "numSms")] + \
-               [("eps", f32), ("usePdl", u32), ("moeFirstExpert", u32), ("moeNumLocal", u32), ("wType", u32)]
+               [("eps", f32), ("usePdl", u32), ("moeFirstExpert", u32), ("moeNumLocal", u32), ("wType", u32), ("hiddenAct", u32)]
 
 
 class LayerPtrs(C.Structure):
@@ -70,6 +70,8 @@ def lib() -> C.CDLL:
     L.dl_engine_set_globals.restype = i32
     L.dl_engine_enable_mega.argtypes = [vp, i32]
     L.dl_engine_enable_mega.restype = i32
+    L.dl_engine_set_vocab_limit.argtypes = [vp, u32]
+    L.dl_engine_set_vocab_limit.restype = i32
     L.dl_engine_set_comm.argtypes = [vp, C.POINTER(CommPtrs)]
     L.dl_engine_set_comm.restype = i32
     for name, args in (("dl_comm_alloc", [C.c_size_t, C.POINTER(vp)]), ("dl_comm_free", [vp]), ("dl_comm_ipc_handle", [vp, vp]),

@@ -89,7 +89,8 @@ class Engine:
                               nActiveExperts=h.n_active_experts, maxBatch=max_batch, nSplits=n_splits, rank=w.rank,
                               nRanks=w.n_ranks, numSms=self.num_sms, eps=h.norm_epsilon, usePdl=1 if use_pdl else 0,
                               moeFirstExpert=w.first_expert, moeNumLocal=w.n_local_experts,
-                              wType=getattr(w, "weight_kind", 0))
+                              wType=getattr(w, "weight_kind", 0),
+                              hiddenAct=1 if int(h.hidden_act) == 0 else 0)   # header: ACT_GELU = 0, ACT_SILU = 1
         self._lib = cl.lib()
         self._h = self._lib.dl_engine_create(C.byref(cfg))
         for l, L in enumerate(w.layers):
@@ -141,6 +142,12 @@ class Engine:
                 self._h = None
         except Exception:
             pass
+
+    def set_vocab_limit(self, limit: int):
+        """Greedy arg-max on the device never returns ids >= limit (the tokenizer's vocabulary size: embeddings may be padded
+        beyond it, reference src/app.cpp:243-246 builds its sampler on the tokenizer size too)."""
+        cl.check(self._lib.dl_engine_set_vocab_limit(self._h, int(limit)), "engine_set_vocab_limit")
+        self._graph_ready = False
 
     def enable_mega(self, enable: bool = True):
         """Single-token forwards through the persistent per-token kernel (dense models). Re-captures the decode graph."""

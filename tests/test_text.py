@@ -30,6 +30,23 @@ def test_tokenizer_file_roundtrip(tmp_path):
     assert r.max_token_length == 4 and r.add_bos
 
 
+def test_tokenizer_file_legacy_chat_stop_key(tmp_path):
+    """Old `.t` files carry key 8 (CHAT_STOP = length of an ignored stop string stored right after the header). The bytes are
+    skipped once the whole header has been read (reference src/tokenizer.cpp:68-86), not in the middle of the key/value table."""
+    import struct
+    vocab = [b"a", b"b", b"ab", b"<s>", b"</s>"]
+    stop, template = b"<|stop|>", b"{{ '[INST]' }}"
+    kv = [(3, 3), (0, 1), (8, len(stop)), (1, len(vocab)), (2, 4), (7, len(template)), (9, 1), (10, 1)]   # key 8 sits mid-table
+    blob = struct.pack("<ii", 0x567124, 8 + 8 * len(kv)) + b"".join(struct.pack("<ii", k, v) for k, v in kv)
+    blob += stop + template + struct.pack("<i", 4)
+    for i, t in enumerate(vocab):
+        blob += struct.pack("<fI", -float(i), len(t)) + t
+    p = tmp_path / "legacy.t"
+    p.write_bytes(blob)
+    r = host().read_tokenizer_file(str(p))
+    assert r.vocab == vocab and r.bos_id == 3 and r.eos_ids == [4] and bytes(r.chat_template) == template and r.add_bos
+
+
 def test_encode_decode_roundtrip(tok):
     text = "Hello world, the model is a llama! ünïcödé ✓ 😃"
     ids = tok.encode(text, True, True)
