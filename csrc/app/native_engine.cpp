@@ -281,7 +281,7 @@ void NativeEngine::prefill(const std::vector<int32_t> &tokens, uint32_t pos) {
         if (tc && rem >= 9) {
             n = (uint32_t)std::min<size_t>(rem, maxPrefill_);
             setInputs(tokens.data() + i, n, pos + (uint32_t)i, true);
-            engCheck(dl_engine_prefill(impl_->engine, n, 0, impl_->stream), "dl_engine_prefill");
+            engCheck(dl_engine_prefill(impl_->engine, n, pos + (uint32_t)i, 0, impl_->stream), "dl_engine_prefill");
         } else {
             n = 1;
             while (n * 2 <= std::min<size_t>(rem, maxBatch_)) n *= 2;

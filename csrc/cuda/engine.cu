@@ -33,6 +33,7 @@ struct Engine {
     unsigned int *megaCounter = nullptr;
     bool useMega = false;
     uint32_t vocabLimit = 0;     // 0 = none; otherwise the greedy arg-max ignores vocabulary rows >= vocabLimit
+    bool tcAttn = true;          // prefill attention on tcgen05 (DL_NO_TC_ATTN=1: per-token CUDA-core kernel)
     bool fusedAttn = true, fusedArgmax = true, useTma = true;   // debugging switches (DL_NO_FUSED_ATTN / DL_NO_FUSED_ARGMAX / DL_NO_TMA)
 };
 
@@ -224,7 +225,7 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
 }
 
 // Prompt chunk of T <= maxPrefill tokens on the tensor-core path. Logits (optional) are produced for the last token.
-static int enginePrefill(Engine &e, uint32_t T, int wantLogits, cudaStream_t stream) {
+static int enginePrefill(Engine &e, uint32_t T, uint32_t p0, int wantLogits, cudaStream_t stream) {
     const EngineConfig &c = e.cfg;
     const GlobalPtrs &g = e.g;
     const bool pdl = false;   // plain stream order between the heterogeneous kernels of this path
@@ -249,11 +250,23 @@ static int enginePrefill(Engine &e, uint32_t T, int wantLogits, cudaStream_t str
         r.eps = c.eps; r.nHeads = c.nHeads; r.nKvHeads = c.nKvHeads; r.headDim = c.headDim; r.seqLen = c.seqLen;
         r.kCache = (__nv_bfloat16 *)L.kCache; r.vCache = (__nv_bfloat16 *)L.vCache;
         DL_TRY(launchRopeKv(r, (int)T, stream, pdl));
-        AttnArgs t{};
-        t.qkv = g.pqkv; t.qkvStride = qkvDim; t.pos = g.pPos; t.kCache = r.kCache; t.vCache = r.vCache;
-        t.nHeads = c.nHeads; t.nKvHeads = c.nKvHeads; t.headDim = c.headDim; t.seqLen = c.seqLen; t.nSplits = 1;
-        t.partial = g.pAttnPartial; t.counters = g.pAttnCounters; t.out = nullptr; t.outStride = qDim; t.outBf16 = (__nv_bfloat16 *)g.pzb;
-        DL_TRY(launchAttnDecode(t, (int)T, stream, pdl));
+        int attnRc = 1;
+        if (e.tcAttn) {
+            // tensor-core attention over the whole chunk: the tokens of a chunk sit at consecutive positions p0 .. p0 + T - 1
+            AttnPrefillArgs ap{};
+            ap.qkv = g.pqkv; ap.qkvStride = qkvDim; ap.T = T; ap.p0 = p0; ap.nHeads = c.nHeads; ap.nKvHeads = c.nKvHeads;
+            ap.headDim = c.headDim; ap.seqLen = c.seqLen; ap.kCache = r.kCache; ap.vCache = r.vCache;
+            ap.out = (__nv_bfloat16 *)g.pzb; ap.outStride = qDim;
+            attnRc = launchAttnPrefillTc(ap, stream);
+            if (attnRc < 0) return attnRc;
+        }
+        if (attnRc == 1) {
+            AttnArgs t{};
+            t.qkv = g.pqkv; t.qkvStride = qkvDim; t.pos = g.pPos; t.kCache = r.kCache; t.vCache = r.vCache;
+            t.nHeads = c.nHeads; t.nKvHeads = c.nKvHeads; t.headDim = c.headDim; t.seqLen = c.seqLen; t.nSplits = 1;
+            t.partial = g.pAttnPartial; t.counters = g.pAttnCounters; t.out = nullptr; t.outStride = qDim; t.outBf16 = (__nv_bfloat16 *)g.pzb;
+            DL_TRY(launchAttnDecode(t, (int)T, stream, pdl));
+        }
         if (tp) { arP.parity = 0; DL_TRY(gemmQ40TcAr(L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, arP)); }
         else DL_TRY(gemmQ40Tc(GEPI_RESIDUAL_, L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, pdl));
         DL_TRY(launchRmsNormBf16(g.px, c.dim, L.norm1, g.pxn, c.dim, c.dim, c.eps, T, stream));
@@ -283,6 +296,7 @@ DL_EXPORT void *dl_engine_create(const dl::EngineConfig *cfg) {
     e->fusedAttn = std::getenv("DL_NO_FUSED_ATTN") == nullptr;
     e->fusedArgmax = std::getenv("DL_NO_FUSED_ARGMAX") == nullptr;
     e->useTma = std::getenv("DL_NO_TMA") == nullptr;
+    e->tcAttn = std::getenv("DL_NO_TC_ATTN") == nullptr;
     if (e->cfg.numSms == 0) {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
@@ -423,8 +437,8 @@ DL_EXPORT int dl_engine_forward_part(void *h, int nb, uint32_t layer, int part, 
     return -2;
 }
 
-DL_EXPORT int dl_engine_prefill(void *h, uint32_t T, int wantLogits, cudaStream_t stream) {
-    return dl::enginePrefill(*(Engine *)h, T, wantLogits, stream);
+DL_EXPORT int dl_engine_prefill(void *h, uint32_t T, uint32_t p0, int wantLogits, cudaStream_t stream) {
+    return dl::enginePrefill(*(Engine *)h, T, p0, wantLogits, stream);
 }
 
 // Captures one greedy decode step (forward of 1 token + argmax + position advance) into a graph.

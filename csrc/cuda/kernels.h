@@ -89,6 +89,18 @@ struct AttnArgs {
 };
 int launchAttnDecode(const AttnArgs &a, int nb, cudaStream_t stream, bool pdl);
 
+// Prompt-chunk attention on tcgen05 (attn_prefill_tc.cu): T consecutive tokens at positions p0.., causal, GQA heads packed on MMA-M.
+struct AttnPrefillArgs {
+    const float *qkv;            // [T][qkvStride] f32, q rows already normalised + rotated; K/V of the chunk already in the cache
+    uint32_t qkvStride;
+    uint32_t T, p0;
+    uint32_t nHeads, nKvHeads, headDim, seqLen;
+    const __nv_bfloat16 *kCache, *vCache;   // [nKvHeads][seqLen][headDim]
+    __nv_bfloat16 *out;          // [T][outStride], head h at columns h * headDim
+    uint32_t outStride;
+};
+int launchAttnPrefillTc(const AttnPrefillArgs &a, cudaStream_t stream);   // 1: shape not covered
+
 // Single-token decode attention with QK-norm + RoPE + KV-cache append fused in (no separate rope kernel).
 struct AttnFusedArgs {
     const float *qkv;        // raw q|k|v row of the token (f32, straight from the QKV GEMV)

@@ -2,8 +2,9 @@
 
 Process model on the B200 box: one process per GPU. Rank 0 is the *root* (tokenizer, sampler, user I/O), ranks >= 1 are
 *workers*: they hold their tensor-parallel weight slices and mirror every forward the root issues. Control flows as the
-reference's 8-byte LlmControlPacket {position, batchSize} (src/app.hpp:46-49) — here extended with an opcode and broadcast
-with torch.distributed; batchSize == 0 is the stop signal. All activation traffic happens inside the kernels over NVLink.
+reference's 8-byte LlmControlPacket {position, batchSize} (src/app.hpp:46-49) — here extended with an opcode and passed through a
+shared-memory channel with heartbeats (parallel/control.py; torch.distributed broadcasts only when the ranks span hosts);
+op 0 is the stop signal. All activation traffic happens inside the kernels over NVLink.
 """
 from __future__ import annotations
 
@@ -19,7 +20,7 @@ from .. import host
 from ..api import InferenceSession
 from .args import AppArgs
 
-OP_STOP, OP_PREFILL, OP_STEP_LOGITS, OP_STEP_GREEDY = 0, 1, 2, 3
+OP_STOP, OP_PREFILL, OP_STEP_LOGITS, OP_STEP_GREEDY, OP_DECODE_N = 0, 1, 2, 3, 4
 
 
 def world():
@@ -45,19 +46,45 @@ def init_distributed_from_env():
     return Communicator()
 
 
-class RootInference:
-    """Root-side handle (reference RootLlmInference, src/app.cpp:168-208): every call first tells the workers what to run."""
+def open_control_channel(comm):
+    """Creates (rank 0) / attaches to (workers) the shared-memory control channel of the job. DL_CONTROL=nccl keeps the
+    torch.distributed broadcasts (needed when the ranks do not share a host)."""
+    if comm is None or os.environ.get("DL_CONTROL") == "nccl" or not getattr(comm, "single_node", True):
+        return None
+    import torch.distributed as dist
+    from ..parallel.control import ControlChannel
+    name = [None]
+    chan = None
+    if comm.rank == 0:
+        chan = ControlChannel(0, comm.world_size)
+        name[0] = chan.name
+    dist.broadcast_object_list(name, src=0)
+    if comm.rank != 0:
+        chan = ControlChannel(comm.rank, comm.world_size, name=name[0])
+    chan.start_heartbeat()
+    dist.barrier()
+    return chan
 
-    def __init__(self, sess: InferenceSession, comm):
+
+class RootInference:
+    """Root-side handle (reference RootLlmInference, src/app.cpp:168-208): every call first tells the workers what to run.
+    The packet travels through shared memory (parallel/control.py); the activations never leave the GPUs."""
+
+    def __init__(self, sess: InferenceSession, comm, chan=None):
         self.sess = sess
         self.comm = comm
+        self.chan = chan
         self.eng = sess.engine
         self.header = sess.header
         self.eval_ms = 0.0
-        self._ctl = torch.zeros(4, dtype=torch.int64, device=sess.device) if comm is not None else None
+        self._ctl = torch.zeros(4, dtype=torch.int64, device=sess.device) if (comm is not None and chan is None) else None
+        self._pin_out = torch.zeros(1, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
 
     def _send(self, op: int, pos: int, tokens: Sequence[int]):
         if self.comm is None:
+            return
+        if self.chan is not None:
+            self.chan.send(op, pos, tokens)
             return
         import torch.distributed as dist
         n = len(tokens)
@@ -80,26 +107,44 @@ class RootInference:
         self._send(OP_STEP_GREEDY, pos, [token])
         self.eng._set_inputs([token], pos)
         self.eng.run_decode_step()
-        return int(self.eng.tokens[0].item())
+        self._pin_out.copy_(self.eng.tokens[:1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return int(self._pin_out[0])
+
+    def decode_greedy(self, token: int, pos: int, n_steps: int) -> List[int]:
+        """n greedy steps with the token fed back on the device (no host round trip per step): one control packet for all."""
+        self._send(OP_DECODE_N, pos, [token, n_steps])
+        return self.eng.decode_greedy(token, pos, n_steps)
 
     def finish(self):
-        self._send(OP_STOP, 0, [])
+        try:
+            self._send(OP_STOP, 0, [])
+        finally:
+            if self.chan is not None:
+                self.chan.close()
 
 
-def worker_loop(sess: InferenceSession, comm) -> None:
+def worker_loop(sess: InferenceSession, comm, chan=None) -> None:
     """Worker main loop (reference runWorkerApp, src/app.cpp:306-365): mirror the root's forwards until the stop packet."""
     import torch.distributed as dist
-    ctl = torch.zeros(4, dtype=torch.int64, device=sess.device)
+    ctl = torch.zeros(4, dtype=torch.int64, device=sess.device) if chan is None else None
     eng = sess.engine
     while True:
-        dist.broadcast(ctl, 0)
-        op, pos, n = int(ctl[0]), int(ctl[1]), int(ctl[2])
+        if chan is not None:
+            op, pos, toks = chan.recv()
+        else:
+            dist.broadcast(ctl, 0)
+            op, pos, n = int(ctl[0]), int(ctl[1]), int(ctl[2])
+            toks = []
+            if op != OP_STOP and n:
+                t = torch.zeros(n, dtype=torch.int64, device=sess.device)
+                dist.broadcast(t, 0)
+                toks = t.tolist()
         if op == OP_STOP:
             print("🛑 Stop signal")
+            if chan is not None:
+                chan.close()
             return
-        t = torch.zeros(n, dtype=torch.int64, device=sess.device)
-        dist.broadcast(t, 0)
-        toks = t.tolist()
         if op == OP_PREFILL:
             eng.prefill(toks, pos, want_logits=False)
         elif op == OP_STEP_LOGITS:
@@ -107,6 +152,8 @@ def worker_loop(sess: InferenceSession, comm) -> None:
         elif op == OP_STEP_GREEDY:
             eng._set_inputs(toks, pos)
             eng.run_decode_step()
+        elif op == OP_DECODE_N:
+            eng.decode_greedy(toks[0], pos, toks[1])
 
 
 @dataclass
@@ -133,8 +180,9 @@ def run_inference_app(args: AppArgs, handler: Callable[[AppContext], None]) -> N
         raise RuntimeError("This version supports only Q40 weights with Q80 sync type")
     sess = InferenceSession(args.model, args.tokenizer, max_seq_len=args.max_seq_len, temperature=args.temperature,
                             topp=args.topp, seed=args.seed, comm=comm, moe_mode=getattr(args, "moe_mode", "auto") or "auto")
+    chan = open_control_channel(comm)
     if rank != 0:
-        worker_loop(sess, comm)
+        worker_loop(sess, comm, chan)
         return
     tok = sess.tokenizer
     if args.info:
@@ -147,7 +195,7 @@ def run_inference_app(args: AppArgs, handler: Callable[[AppContext], None]) -> N
         name = torch.cuda.get_device_name(sess.device)
         print(f"🧠 GPU: {name} x{n_nodes} (sm_100a kernels; tensor parallel over NVLink peer memory)")
         print("💿 Weights loaded")
-    inf = RootInference(sess, comm)
+    inf = RootInference(sess, comm, chan)
     ctx = AppContext(args=args, sess=sess, inference=inf, tokenizer=tok, sampler=sess.sampler, header=header)
     try:
         handler(ctx)

@@ -60,6 +60,8 @@ def lib() -> C.CDLL:
     L.dl_gemm_q40_tc.restype = i32
     L.dl_rmsnorm_bf16.argtypes = [vp, u32, vp, vp, u32, u32, f32, u32, vp]
     L.dl_rmsnorm_bf16.restype = i32
+    L.dl_attn_prefill_tc.argtypes = [vp, u32, u32, u32, u32, u32, u32, u32, vp, vp, vp, u32, vp]
+    L.dl_attn_prefill_tc.restype = i32
     L.dl_engine_create.argtypes = [C.POINTER(EngineConfig)]
     L.dl_engine_create.restype = vp
     L.dl_engine_destroy.argtypes = [vp]
@@ -104,7 +106,7 @@ def lib() -> C.CDLL:
     L.dl_engine_forward.restype = i32
     L.dl_engine_forward_part.argtypes = [vp, i32, u32, i32, vp, vp]
     L.dl_engine_forward_part.restype = i32
-    L.dl_engine_prefill.argtypes = [vp, u32, i32, vp]
+    L.dl_engine_prefill.argtypes = [vp, u32, u32, i32, vp]
     L.dl_engine_prefill.restype = i32
     L.dl_engine_capture_decode.argtypes = [vp]
     L.dl_engine_capture_decode.restype = i32

@@ -213,7 +213,7 @@ class Engine:
                 last = i + n == len(tokens)
                 self.p_tokens[:n].copy_(torch.tensor(tokens[i:i + n], dtype=torch.int32))
                 self.p_pos[:n].copy_(torch.arange(start_pos + i, start_pos + i + n, dtype=torch.int32))
-                cl.check(self._lib.dl_engine_prefill(self._h, n, 1 if (last and want_logits) else 0, cl.stream_ptr()), "engine_prefill")
+                cl.check(self._lib.dl_engine_prefill(self._h, n, start_pos + i, 1 if (last and want_logits) else 0, cl.stream_ptr()), "engine_prefill")
             else:
                 n = 1
                 while n * 2 <= min(rem, self.max_batch):
