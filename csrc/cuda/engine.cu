@@ -31,6 +31,10 @@ struct Engine {
     bool traceAllCtas = false;   // persistent kernel: every CTA records its phase stamps (skew analysis, tools/trace_mega.py --all)
     MegaLayer *megaLayers = nullptr;   // device copy of the per-layer pointer table for the persistent decode kernel
     unsigned int *megaCounter = nullptr;
+    uint2 *megaX = nullptr, *megaQkv = nullptr, *megaZ = nullptr, *megaH = nullptr;   // LL vectors of the persistent kernel
+    unsigned int *megaSeq = nullptr;
+    unsigned int *abortHost = nullptr, *abortDev = nullptr;   // mapped pinned word: device wait loops report a blown spin budget here
+    uint32_t megaCtas = 0;             // DL_MEGA_CTAS: grid size override of the persistent kernel (0 = one CTA per SM)
     bool useMega = false;
     uint32_t vocabLimit = 0;     // 0 = none; otherwise the greedy arg-max ignores vocabulary rows >= vocabLimit
     bool tcAttn = true;          // prefill attention on tcgen05 (DL_NO_TC_ATTN=1: per-token CUDA-core kernel)
@@ -46,6 +50,7 @@ struct Engine {
 static void fillAr(const Engine &e, ArArgs &ar, uint32_t parity) {
     const CommPtrs &c = e.comm;
     ar.nRanks = c.nRanks; ar.rank = c.rank; ar.parity = parity; ar.maxCtas = c.maxCtas; ar.slotStride = c.slotStride; ar.dim = e.cfg.dim;
+    ar.slotsMc = c.mcArena ? (uint64_t *)((uint8_t *)c.mcArena + c.slotsOff) : nullptr;
     for (uint32_t r = 0; r < c.nRanks && r < (uint32_t)kMaxRanks; r++) {
         uint8_t *base = (uint8_t *)c.arena[r];
         ar.slots[r] = (uint64_t *)(base + c.slotsOff);
@@ -106,7 +111,8 @@ static int engineDecodeMega(Engine &e, bool greedyAdvance, cudaStream_t stream) 
     m.embedding = e.g.embedding; m.finalNorm = e.g.finalNorm; m.rope = e.g.rope;
     m.wclsQs = (const uint8_t *)e.g.wclsQs; m.wclsSc = (const uint8_t *)e.g.wclsSc;
     m.tokens = e.g.tokens; m.pos = e.g.pos; m.history = e.g.history;
-    m.x = e.g.x; m.qkv = e.g.qkv; m.z = e.g.z; m.h = e.g.h; m.logits = e.g.logits;
+    m.logits = e.g.logits;
+    m.xW = e.megaX; m.qkvW = e.megaQkv; m.zW = e.megaZ; m.hW = e.megaH; m.launchSeq = e.megaSeq; m.abortFlag = e.abortDev;
     m.attnPartial = e.g.attnPartial; m.attnCounters = e.g.attnCounters;
     m.argVal = e.g.argVal; m.argIdx = e.g.argIdx; m.argCounter = e.g.argCounter; m.gridCounter = e.megaCounter;
     m.rowOffsetGlobal = c.rank * c.vocab; m.greedyAdvance = greedyAdvance ? 1u : 0u; m.vocabLimit = e.vocabLimit;
@@ -114,7 +120,7 @@ static int engineDecodeMega(Engine &e, bool greedyAdvance, cudaStream_t stream) 
     m.traceCtas = e.traceAllCtas ? c.numSms : 1u;
     m.traceStride = e.traceAllCtas ? (uint32_t)(((size_t)e.traceCap * 4) / c.numSms) : 0u;
     if (e.comm.nRanks > 1) fillAr(e, m.ar, 0);
-    return launchMegaDecode(m, (int)c.numSms, stream);
+    return launchMegaDecode(m, (int)(e.megaCtas ? e.megaCtas : c.numSms), stream);
 }
 
 // logitsMode: 0 = none (prefill chunk), 1 = logits of the last token in the batch into logits[0], 2 = all tokens
@@ -313,6 +319,8 @@ DL_EXPORT void dl_engine_destroy(void *h) {
     if (e->captureStream) cudaStreamDestroy(e->captureStream);
     if (e->megaLayers) cudaFree(e->megaLayers);
     if (e->megaCounter) cudaFree(e->megaCounter);
+    for (void *q : {(void *)e->megaX, (void *)e->megaQkv, (void *)e->megaZ, (void *)e->megaH, (void *)e->megaSeq}) if (q) cudaFree(q);
+    if (e->abortHost) cudaFreeHost(e->abortHost);
     delete e;
 }
 
@@ -345,6 +353,24 @@ DL_EXPORT int dl_engine_enable_mega(void *h, int enable) {
         DL_CUDA_CHECK(cudaMemcpy(e->megaLayers, tab.data(), tab.size() * sizeof(dl::MegaLayer), cudaMemcpyHostToDevice));
         DL_CUDA_CHECK(cudaMalloc(&e->megaCounter, 256));
         DL_CUDA_CHECK(cudaMemset(e->megaCounter, 0, 256));
+        const dl::EngineConfig &c = e->cfg;
+        const size_t qDim = (size_t)c.nHeads * c.headDim, qkvDim = qDim + 2 * (size_t)c.nKvHeads * c.headDim;
+        auto allocW = [](uint2 **p, size_t n) {
+            const size_t bytes = (n + 8) * sizeof(uint2);
+            if (cudaMalloc(p, bytes) != cudaSuccess) return false;
+            return cudaMemset(*p, 0, bytes) == cudaSuccess;
+        };
+        if (!allocW(&e->megaX, c.dim) || !allocW(&e->megaQkv, qkvDim) || !allocW(&e->megaZ, qDim) || !allocW(&e->megaH, c.ffDim)) return -41;
+        DL_CUDA_CHECK(cudaMalloc(&e->megaSeq, 256));
+        const unsigned int one = 1;
+        DL_CUDA_CHECK(cudaMemset(e->megaSeq, 0, 256));
+        DL_CUDA_CHECK(cudaMemcpy(e->megaSeq, &one, sizeof(one), cudaMemcpyHostToDevice));   // epochs start at 1024: never equal to the zeroed words
+        if (!e->abortHost) {
+            DL_CUDA_CHECK(cudaHostAlloc((void **)&e->abortHost, 64, cudaHostAllocMapped));
+            *e->abortHost = 0;
+            DL_CUDA_CHECK(cudaHostGetDevicePointer((void **)&e->abortDev, e->abortHost, 0));
+        }
+        if (const char *g = std::getenv("DL_MEGA_CTAS")) e->megaCtas = (uint32_t)std::atoi(g);
     }
     e->useMega = enable != 0;
     return 0;
@@ -355,6 +381,12 @@ DL_EXPORT int dl_engine_set_vocab_limit(void *h, uint32_t limit) {
     if (e->vocabLimit != limit && e->decodeGraph) { cudaGraphExecDestroy(e->decodeGraph); e->decodeGraph = nullptr; }   // the limit is baked into the captured launch
     e->vocabLimit = limit;
     return 0;
+}
+
+// 1 when a device-side wait loop gave up (dead peer rank, CTA that never became resident): the results of that step are invalid.
+DL_EXPORT int dl_engine_aborted(void *h) {
+    Engine *e = (Engine *)h;
+    return (e->abortHost && *e->abortHost) ? 1 : 0;
 }
 
 DL_EXPORT int dl_engine_set_comm(void *h, const dl::CommPtrs *p) {

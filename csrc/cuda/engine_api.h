@@ -67,6 +67,7 @@ struct GlobalPtrs {
 struct CommPtrs {   // mirrored by ctypes
     uint32_t nRanks, rank, maxCtas, slotStride;
     void *arena[kApiMaxRanks];          // every rank's symmetric arena mapped into this process
+    void *mcArena;                      // NVLS multicast mapping of the arena (null: none)
     uint64_t slotsOff, flagsOff, candValOff, candIdxOff, candFlagOff, gatherOff;
     uint64_t prefillSlotsOff;        // LL slots for the prefill GEMM all-reduce: [2][nRanks][maxPrefill * dim]
     uint32_t prefillSlotStride;
@@ -82,6 +83,7 @@ int dl_engine_set_globals(void *h, const dl::GlobalPtrs *p);
 int dl_engine_set_comm(void *h, const dl::CommPtrs *p);
 int dl_engine_enable_mega(void *h, int enable);
 int dl_engine_set_vocab_limit(void *h, uint32_t limit);   // greedy arg-max never returns ids >= limit (tokenizer vocabulary size)
+int dl_engine_aborted(void *h);
 int dl_engine_set_trace(void *h, uint64_t *buf, uint32_t capLaunches);
 int dl_engine_set_trace_all(void *h, int allCtas);
 uint32_t dl_engine_num_sms(void *h);

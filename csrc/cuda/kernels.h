@@ -17,6 +17,7 @@ struct ArArgs {
     uint32_t dim;                 // words between tokens inside a slot
     uint64_t *slots[kMaxRanks];   // rank r's LL slot area, mapped into this process: [2][nRanks][slotStride] x (f32 payload, flag)
     uint64_t *cand[kMaxRanks];    // rank r's arg-max candidates: [nRanks] x (f32 value, index + 1)
+    uint64_t *slotsMc;            // NVLS multicast mapping of the slot area (one multimem.st reaches every rank), or null
 };
 
 struct GemvArgs {
@@ -156,7 +157,10 @@ struct MegaArgs {
     const float *embedding, *finalNorm, *rope;
     const uint8_t *wclsQs, *wclsSc;
     int *tokens, *pos, *history;
-    float *x, *qkv, *z, *h, *logits;
+    float *logits;
+    uint2 *xW, *qkvW, *zW, *hW;  // phase-crossing vectors as LL words {f32, epoch} (engine-owned, see mega_decode.cu)
+    unsigned int *launchSeq;     // device-resident launch counter (epoch base)
+    unsigned int *abortFlag;     // host-mapped: set by a wait loop that ran out of its spin budget
     float *attnPartial;
     unsigned int *attnCounters;
     float *argVal;

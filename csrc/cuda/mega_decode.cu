@@ -6,9 +6,17 @@
 //     through a single shared-memory ring with cp.async.bulk + mbarriers. It never synchronises with the phases — only
 //     ring space limits it — so the HBM stream runs continuously across phase boundaries and layers.
 //   * warps 0-15 (consumers) execute the phases embedding -> per layer [QKV GEMV | attention | WO GEMV + residual |
-//     W1|W3 GEMV + SwiGLU | W2 GEMV + residual] -> logits GEMV + arg-max, separated by software grid barriers (one atomic
-//     arrive + acquire spin, ~1 µs). Activation reads bypass L1 (ld.global.cg): L1 is not invalidated inside a launch.
-//   * tensor-parallel runs use the same LL-word all-reduce in the WO / W2 epilogues and the cross-rank arg-max.
+//     W1|W3 GEMV + SwiGLU | W2 GEMV + residual] -> logits GEMV + arg-max, separated by software grid barriers.
+//   * Every vector that crosses a phase boundary (x, q|k|v, z, h) travels as LL words: 8-byte {f32 payload, epoch} stores that
+//     L2 delivers atomically. The barrier therefore needs NO memory fence (a relaxed arrive + relaxed poll): it only orders
+//     control flow, and a consumer that finds a word with a stale epoch simply re-reads it. Measured on B200 with the weight
+//     stream running (profiles/barrier_microbench.txt): fenced barrier 2.2 us, relaxed 0.9 us — MEMBAR.GPU queues behind the
+//     ~180 KB of bulk-copy reads each SM keeps in flight. Round 1 tried LL words *instead of* barriers and lost (every thread
+//     polling during the arrival skew floods L2, experiments/README.md); here the poll starts only after the arrival counter
+//     says the stores have been issued, so it almost always succeeds on the first read.
+//   * tensor-parallel runs use the same LL-word protocol between GPUs in the WO / W2 epilogues (one multimem.st through the
+//     NVSwitch multicast mapping reaches every rank; unicast peer stores when no multicast object exists) and the cross-rank
+//     arg-max.
 // The kernel takes over the roles of NnExecutor's step loop + barriers (reference src/nn/nn-executor.cpp:137-175) on the GPU.
 #include "kernels.h"
 #include "tma_common.cuh"
@@ -27,24 +35,80 @@ static uint32_t megaStageRows(uint32_t n, uint32_t stageBytes) {
 struct MegaSmem {
     uint8_t *ring;
     uint4 *planeA, *planeB;
-    float *dxs, *dx8, *partial, *red;
+    float *dxs, *dx8, *partial, *red, *rope;
     uint64_t *fullBar, *emptyBar;
 };
 
-__device__ __forceinline__ void gridBarrier(unsigned int *ctr, unsigned int &target, int tid) {
-    consumerBarrier();   // orders every consumer thread's global writes before thread 0's release below
+// Spin budget of every wait loop in this kernel: a peer rank that died or a CTA that never became resident must not wedge the GPU.
+// After ~2^27 polls (seconds) the waiter raises the abort flag (host-visible); every loop also leaves as soon as the flag is up,
+// so the kernel drains and the host reports the failure (reference: socket exceptions, src/nn/nn-network.cpp:84-123).
+constexpr uint32_t kSpinCheck = 1u << 12;
+constexpr uint32_t kSpinLimit = 1u << 27;
+
+struct SpinGuard {
+    volatile unsigned int *abortFlag;
+    uint32_t n = 0;
+    __device__ __forceinline__ explicit SpinGuard(unsigned int *f) : abortFlag(f) {}
+    // returns true when the caller must stop waiting
+    __device__ __forceinline__ bool tick() {
+        if ((++n & (kSpinCheck - 1)) != 0) return false;
+        if (abortFlag && *abortFlag) return true;
+        if (n >= kSpinLimit) {
+            if (abortFlag) *abortFlag = 1u;
+            return true;
+        }
+        return false;
+    }
+};
+
+// Control-only grid barrier: relaxed arrive, relaxed poll. Data crossing it is self-validating (LL words), see the file header.
+__device__ __forceinline__ void gridBarrier(unsigned int *ctr, unsigned int &target, int tid, unsigned int *abortFlag) {
+    consumerBarrier();   // every consumer thread has issued its stores of this phase
     if (tid == 0) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         target += gridDim.x;
         unsigned int v;
+        SpinGuard g(abortFlag);
         do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        } while (v < target);
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target && !g.tick());
     }
     consumerBarrier();
 }
 
-__device__ __forceinline__ float4 ldcg4(const float4 *p) { return __ldcg(p); }
+// ---- LL words inside one GPU: {f32 payload, epoch} in one 8-byte store; readers compare the epoch ----
+__device__ __forceinline__ void stW(uint2 *p, float v, uint32_t epoch) {
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint4 ldW2(const uint2 *p) {   // two consecutive words
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 ldW(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+// One value, polled until its epoch matches.
+__device__ __forceinline__ float ldWwait(const uint2 *p, uint32_t epoch, unsigned int *abortFlag) {
+    uint2 v = ldW(p);
+    if (v.y != epoch) {
+        SpinGuard g(abortFlag);
+        do { v = ldW(p); } while (v.y != epoch && !g.tick());
+    }
+    return __uint_as_float(v.x);
+}
+// Four consecutive values (index i4 * 4 ..), polled until all four epochs match.
+__device__ __forceinline__ float4 ldW4wait(const uint2 *base, uint32_t i4, uint32_t epoch, unsigned int *abortFlag) {
+    const uint2 *p = base + (size_t)i4 * 4;
+    uint4 a = ldW2(p), b = ldW2(p + 2);
+    if (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch) {
+        SpinGuard g(abortFlag);
+        do { a = ldW2(p); b = ldW2(p + 2); } while ((a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch) && !g.tick());
+    }
+    return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+}
 
 // Ring position shared (by construction) by the producer and the consumers: stage index + mbarrier phase parity, advanced
 // once per fill. Kept incrementally — the hot loop contains no integer division (every `%`/`/` by a runtime value costs a
@@ -64,9 +128,11 @@ __device__ __forceinline__ void megaTile(const MegaPhase &P, uint32_t &pairBegin
 }
 
 // One GEMV phase on the consumer warps.
+// `in` / inEpoch: LL vector consumed by the prologue; `outW` / outEpoch: LL vector produced by the epilogue (EPI_RESIDUAL: the
+// residual stream itself, read-modify-written on the rows this CTA owns); `outF`: plain f32 output of the logits phase.
 template <int PRO, int EPI>
-__device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase &P, const float *in, const float *normW, float *out,
-                         uint32_t arParity, RingPos &ring, int tid, uint32_t &slot) {
+__device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase &P, const uint2 *in, uint32_t inEpoch, const float *normW,
+                         uint2 *outW, uint32_t outEpoch, float *outF, uint32_t arParity, RingPos &ring, int tid, uint32_t &slot) {
     auto stamp = [&]() { if (m.trace && tid == 0 && blockIdx.x < m.traceCtas) m.trace[(size_t)blockIdx.x * m.traceStride + slot] = globalTimerNs(); slot++; };
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t n = P.n;
@@ -79,68 +145,74 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
     uint4 *planeA = sm.planeA, *planeB = sm.planeB;
     float *dxs = sm.dxs, *dx8 = sm.dx8, *partial = sm.partial, *red = sm.red;
 
-    // ---- prologue: (rmsnorm) + q80 quantisation of the activation vector (one pass: the vector stays in registers) ----
+    // The residual of the rows this CTA owns is fetched now, so that its L2 round trip overlaps the prologue and the main loop
+    // (own rows were written by this very thread in the previous residual phase / the embedding phase: no epoch check needed).
+    float resid = 0.f;
+    if (EPI == EPI_RESIDUAL_ && (uint32_t)tid < tileRows) resid = __uint_as_float(ldW(outW + rowBase + tid).x);
+
+    // ---- prologue: (rmsnorm) + q80 quantisation of the activation vector. RMS-norm phases (n = dim <= 8192) keep the whole
+    // vector in registers for the reduction; plain phases stream it in chunks of 16384 elements (any n) ----
     {
         const uint32_t nVec = n / 4;
-        const float4 *x4 = reinterpret_cast<const float4 *>(in);
-        // plain phases: 8 float4 x 512 threads = 16384 elements; RMS-norm phases (n = dim <= 8192) hold the norm weights in the
-        // other half of that register budget, loaded together with x so only one L2 round trip sits on the critical path
         constexpr int kMaxVec = PRO == PRO_RMSNORM_ ? 4 : 8;
-        float4 xv[kMaxVec];
-        float4 wv[PRO == PRO_RMSNORM_ ? kMaxVec : 1];
-        if (PRO == PRO_RMSNORM_) {
-#pragma unroll
-            for (int k = 0; k < kMaxVec; k++) {
-                const uint32_t i = k * kConsumerThreads + tid;
-                wv[k] = i < nVec ? __ldg(reinterpret_cast<const float4 *>(normW) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        float ss = 0.f;
-#pragma unroll
-        for (int k = 0; k < kMaxVec; k++) {
-            const uint32_t i = k * kConsumerThreads + tid;
-            xv[k] = i < nVec ? ldcg4(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            ss += xv[k].x * xv[k].x + xv[k].y * xv[k].y + xv[k].z * xv[k].z + xv[k].w * xv[k].w;
-        }
-        float inv = 1.f;
-        if (PRO == PRO_RMSNORM_) {
-            ss = consumerSum(ss, red);
-            inv = rsqrtf(ss / (float)n + m.eps);
-        }
+        constexpr uint32_t kChunkVec = kMaxVec * kConsumerThreads;
         uint8_t *pa = reinterpret_cast<uint8_t *>(planeA);
         uint8_t *pb = reinterpret_cast<uint8_t *>(planeB);
+        for (uint32_t vecBase = 0; vecBase < nVec; vecBase += kChunkVec) {
+            float4 xv[kMaxVec];
+            float4 wv[PRO == PRO_RMSNORM_ ? kMaxVec : 1];
+            if (PRO == PRO_RMSNORM_) {
 #pragma unroll
-        for (int k = 0; k < kMaxVec; k++) {
-            const uint32_t i = k * kConsumerThreads + tid;
-            if (k * kConsumerThreads >= nVec) break;     // block-uniform
-            const bool act = i < nVec;
-            float4 v = xv[k];
-            if (PRO == PRO_RMSNORM_ && act) {
-                const float4 w = wv[PRO == PRO_RMSNORM_ ? k : 0];
-                v.x = w.x * (v.x * inv); v.y = w.y * (v.y * inv); v.z = w.z * (v.z * inv); v.w = w.w * (v.w * inv);
+                for (int k = 0; k < kMaxVec; k++) {
+                    const uint32_t i = vecBase + k * kConsumerThreads + tid;
+                    wv[k] = i < nVec ? __ldg(reinterpret_cast<const float4 *>(normW) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
-            float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-            const float dq = amax / 127.f;
-            const float id = dq != 0.f ? 1.f / dq : 0.f;
-            const int q0 = __float2int_rn(v.x * id), q1 = __float2int_rn(v.y * id);
-            const int q2 = __float2int_rn(v.z * id), q3 = __float2int_rn(v.w * id);
-            int qsum = q0 + q1 + q2 + q3;
-            qsum += __shfl_xor_sync(0xffffffffu, qsum, 1);
-            qsum += __shfl_xor_sync(0xffffffffu, qsum, 2);
-            qsum += __shfl_xor_sync(0xffffffffu, qsum, 4);
-            if (act) {
-                const uint32_t b = i >> 3, sub = i & 7, kk = sub >> 1, odd = sub & 1;
-                uint8_t *wa = pa + (size_t)b * 16 + kk * 4 + odd;
-                uint8_t *wb = pb + (size_t)b * 16 + kk * 4 + odd;
-                wa[0] = (uint8_t)(int8_t)q0; wa[2] = (uint8_t)(int8_t)q1;
-                wb[0] = (uint8_t)(int8_t)q2; wb[2] = (uint8_t)(int8_t)q3;
-                if (sub == 0) {
-                    const float dr = __half2float(__float2half_rn(dq));
-                    dxs[b] = dr;
-                    dx8[b] = dr * 8.f * (float)qsum;
+            float ss = 0.f;
+#pragma unroll
+            for (int k = 0; k < kMaxVec; k++) {
+                const uint32_t i = vecBase + k * kConsumerThreads + tid;
+                xv[k] = i < nVec ? ldW4wait(in, i, inEpoch, m.abortFlag) : make_float4(0.f, 0.f, 0.f, 0.f);
+                ss += xv[k].x * xv[k].x + xv[k].y * xv[k].y + xv[k].z * xv[k].z + xv[k].w * xv[k].w;
+            }
+            float inv = 1.f;
+            if (PRO == PRO_RMSNORM_) {
+                ss = consumerSum(ss, red);
+                inv = rsqrtf(ss / (float)n + m.eps);
+            }
+#pragma unroll
+            for (int k = 0; k < kMaxVec; k++) {
+                const uint32_t i = vecBase + k * kConsumerThreads + tid;
+                if (vecBase + k * kConsumerThreads >= nVec) break;     // block-uniform
+                const bool act = i < nVec;
+                float4 v = xv[k];
+                if (PRO == PRO_RMSNORM_ && act) {
+                    const float4 w = wv[PRO == PRO_RMSNORM_ ? k : 0];
+                    v.x = w.x * (v.x * inv); v.y = w.y * (v.y * inv); v.z = w.z * (v.z * inv); v.w = w.w * (v.w * inv);
+                }
+                float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+                const float dq = amax / 127.f;
+                const float id = dq != 0.f ? 1.f / dq : 0.f;
+                const int q0 = __float2int_rn(v.x * id), q1 = __float2int_rn(v.y * id);
+                const int q2 = __float2int_rn(v.z * id), q3 = __float2int_rn(v.w * id);
+                int qsum = q0 + q1 + q2 + q3;
+                qsum += __shfl_xor_sync(0xffffffffu, qsum, 1);
+                qsum += __shfl_xor_sync(0xffffffffu, qsum, 2);
+                qsum += __shfl_xor_sync(0xffffffffu, qsum, 4);
+                if (act) {
+                    const uint32_t b = i >> 3, sub = i & 7, kk = sub >> 1, odd = sub & 1;
+                    uint8_t *wa = pa + (size_t)b * 16 + kk * 4 + odd;
+                    uint8_t *wb = pb + (size_t)b * 16 + kk * 4 + odd;
+                    wa[0] = (uint8_t)(int8_t)q0; wa[2] = (uint8_t)(int8_t)q1;
+                    wb[0] = (uint8_t)(int8_t)q2; wb[2] = (uint8_t)(int8_t)q3;
+                    if (sub == 0) {
+                        const float dr = __half2float(__float2half_rn(dq));
+                        dxs[b] = dr;
+                        dx8[b] = dr * 8.f * (float)qsum;
+                    }
                 }
             }
         }
@@ -231,37 +303,46 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
         return v;
     };
     if (EPI == EPI_SWIGLU_) {
-        for (uint32_t p = tid; p < tileRows / 2; p += kConsumerThreads) out[pairBegin + p] = gateAct(rowSum(2 * p), m.act) * rowSum(2 * p + 1);
+        for (uint32_t p = tid; p < tileRows / 2; p += kConsumerThreads) stW(outW + pairBegin + p, gateAct(rowSum(2 * p), m.act) * rowSum(2 * p + 1), outEpoch);
+    } else if (EPI == EPI_STORE_) {
+        for (uint32_t r = tid; r < tileRows; r += kConsumerThreads) stW(outW + rowBase + r, rowSum(r), outEpoch);
     } else if (EPI == EPI_RESIDUAL_) {
+        // tileRows <= kConsumerThreads (checked on the host): thread r owns row r of the tile
         if (m.ar.nRanks > 1) {
             const ArArgs &ar = m.ar;
             const size_t slotBase = (size_t)(arParity * ar.nRanks + ar.rank) * ar.slotStride;
-            for (uint32_t r = tid; r < tileRows; r += kConsumerThreads) {
+            if ((uint32_t)tid < tileRows) {
+                const uint32_t r = tid;
                 const float v = rowSum(r);
+                if (ar.slotsMc) {
+                    // one store, replicated by the NVSwitch into slot[myRank] of every rank (this one included)
+                    const uint64_t word = (uint64_t)__float_as_uint(v) | (1ull << 32);
+                    asm volatile("multimem.st.relaxed.sys.global.b64 [%0], %1;" ::"l"(ar.slotsMc + slotBase + rowBase + r), "l"(word) : "memory");
+                } else {
 #pragma unroll 1
-                for (uint32_t p = 0; p < ar.nRanks; p++) stLL(ar.slots[(ar.rank + p) % ar.nRanks] + slotBase + rowBase + r, __float_as_uint(v), 1u);
-            }
-            uint64_t *mine = ar.slots[ar.rank];
-            for (uint32_t r = tid; r < tileRows; r += kConsumerThreads) {
+                    for (uint32_t p = 0; p < ar.nRanks; p++) stLL(ar.slots[(ar.rank + p) % ar.nRanks] + slotBase + rowBase + r, __float_as_uint(v), 1u);
+                }
+                uint64_t *mine = ar.slots[ar.rank];
                 float sum = 0.f;
+                SpinGuard g(m.abortFlag);
                 for (uint32_t sr = 0; sr < ar.nRanks; sr++) {
                     uint64_t *w = mine + (size_t)(arParity * ar.nRanks + sr) * ar.slotStride + rowBase + r;
-                    uint2 v = ldLL(w);
-                    while (v.y == 0u) v = ldLL(w);
-                    sum += __uint_as_float(v.x);
+                    uint2 v2 = ldLL(w);
+                    while (v2.y == 0u && !g.tick()) v2 = ldLL(w);
+                    sum += __uint_as_float(v2.x);
                     stLL(w, 0u, 0u);
                 }
-                out[rowBase + r] = __ldcg(out + rowBase + r) + sum;
+                stW(outW + rowBase + r, resid + sum, outEpoch);
             }
-        } else {
-            for (uint32_t r = tid; r < tileRows; r += kConsumerThreads) out[rowBase + r] = __ldcg(out + rowBase + r) + rowSum(r);
+        } else if ((uint32_t)tid < tileRows) {
+            stW(outW + rowBase + tid, resid + rowSum(tid), outEpoch);
         }
     } else {
         float best = -INFINITY;
         int bestIdx = 0x7fffffff;
         for (uint32_t r = tid; r < tileRows; r += kConsumerThreads) {
             const float v = rowSum(r);
-            out[rowBase + r] = v;
+            outF[rowBase + r] = v;
             if (EPI == EPI_ARGMAX_ && v > best && m.rowOffsetGlobal + rowBase + r < m.vocabLimit) { best = v; bestIdx = (int)(m.rowOffsetGlobal + rowBase + r); }
         }
         if (EPI == EPI_ARGMAX_) {
@@ -318,7 +399,8 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
                     if (lane < ar.nRanks) {
                         uint64_t *w = ar.cand[ar.rank] + lane;
                         uint2 v = ldLL(w);
-                        while (v.y == 0u) v = ldLL(w);
+                        SpinGuard g(m.abortFlag);
+                        while (v.y == 0u && !g.tick()) v = ldLL(w);
                         best = __uint_as_float(v.x);
                         bestIdx = (int)(v.y - 1u);
                         stLL(w, 0u, 0u);
@@ -347,7 +429,7 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
 // Attention phase: work items (head, split) are dealt round-robin to the CTAs; the 16 consumer warps of a CTA share the
 // positions of one item. Same math as attnFusedKernel (decode_ops.cu).
 template <int HD>
-__device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaLayer &L, int p, int tid) {
+__device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaLayer &L, int p, int tid, uint32_t inEpoch, uint32_t outEpoch) {
     constexpr int DPL = HD / 32;
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t nPos = (uint32_t)p + 1;
@@ -360,7 +442,8 @@ __device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaL
     float *sM = sm.partial + 16 * HD;         // [16]
     float *sL = sM + 16;                      // [16]
     __shared__ bool sLast;
-    const float2 *ropeRow = reinterpret_cast<const float2 *>(m.rope) + (size_t)p * (HD / 2) + lane * (DPL / 2);
+    // rotary table row of this token's position: staged in shared memory once per launch (it is the same for all layers)
+    const float2 *ropeRow = reinterpret_cast<const float2 *>(sm.rope) + lane * (DPL / 2);
     auto normRope = [&](float *v, const float *nw) {
         if (nw) {
             float ss = 0.f;
@@ -388,8 +471,16 @@ __device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaL
         const bool ownsNew = end == nPos;
         const uint32_t cachedEnd = ownsNew ? end - 1 : end;
         float q[DPL];
+        {
+            const uint2 *src = m.qkvW + (size_t)h * HD + lane * DPL;
+            if constexpr (DPL == 4) {
+                const float4 v = ldW4wait(src, 0, inEpoch, m.abortFlag);
+                q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+            } else {
 #pragma unroll
-        for (int i = 0; i < DPL; i++) q[i] = __ldcg(m.qkv + (size_t)h * HD + lane * DPL + i);
+                for (int i = 0; i < DPL; i++) q[i] = ldWwait(src + i, inEpoch, m.abortFlag);
+            }
+        }
         normRope(q, L.qNorm);
         const float scale = rsqrtf((float)HD);
 #pragma unroll
@@ -401,10 +492,17 @@ __device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaL
         __nv_bfloat16 *vHead = L.vCache + (size_t)kvh * m.seqLen * HD;
         if (ownsNew && warp == 0) {
             float kn[DPL], vn[DPL];
+            {
+                const uint2 *ks = m.qkvW + qDim + (size_t)kvh * HD + lane * DPL;
+                const uint2 *vs = m.qkvW + qDim + kvDim + (size_t)kvh * HD + lane * DPL;
+                if constexpr (DPL == 4) {
+                    const float4 a = ldW4wait(ks, 0, inEpoch, m.abortFlag), b = ldW4wait(vs, 0, inEpoch, m.abortFlag);
+                    kn[0] = a.x; kn[1] = a.y; kn[2] = a.z; kn[3] = a.w;
+                    vn[0] = b.x; vn[1] = b.y; vn[2] = b.z; vn[3] = b.w;
+                } else {
 #pragma unroll
-            for (int i = 0; i < DPL; i++) {
-                kn[i] = __ldcg(m.qkv + qDim + (size_t)kvh * HD + lane * DPL + i);
-                vn[i] = __ldcg(m.qkv + qDim + kvDim + (size_t)kvh * HD + lane * DPL + i);
+                    for (int i = 0; i < DPL; i++) { kn[i] = ldWwait(ks + i, inEpoch, m.abortFlag); vn[i] = ldWwait(vs + i, inEpoch, m.abortFlag); }
+                }
             }
             normRope(kn, L.kNorm);
             __nv_bfloat162 kb[DPL / 2], vb[DPL / 2];
@@ -499,9 +597,9 @@ __device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaL
                 Lsum += sL[w] * wgt;
             }
         }
-        float *outRow = m.z + (size_t)h * HD;
+        uint2 *outRow = m.zW + (size_t)h * HD;
         if (eff == 1) {
-            if (tid < HD) outRow[tid] = num / Lsum;
+            if (tid < HD) stW(outRow + tid, num / Lsum, outEpoch);
             continue;
         }
         float *pOut = m.attnPartial + ((size_t)h * m.nSplits + split) * (HD + 2);
@@ -527,7 +625,7 @@ __device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaL
                     n2 += w * __ldcg(pIn + (size_t)s * (HD + 2) + tid);
                     den += w * __ldcg(pIn + (size_t)s * (HD + 2) + HD + 1);
                 }
-                outRow[tid] = n2 / den;
+                stW(outRow + tid, n2 / den, outEpoch);
             }
         }
     }
@@ -545,7 +643,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_
     sm.dx8 = sm.dxs + m.planeBlocks;
     sm.partial = sm.dx8 + m.planeBlocks;
     sm.red = sm.partial + m.partialFloats;
-    sm.fullBar = reinterpret_cast<uint64_t *>(sm.red + 32);
+    sm.rope = sm.red + 32;                                              // [128] rotary (cos, sin) pairs of this token's position
+    sm.fullBar = reinterpret_cast<uint64_t *>(sm.rope + 128);
     sm.emptyBar = sm.fullBar + kMaxStages;
 
     if (tid == 0) {
@@ -600,50 +699,58 @@ __global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_
     uint32_t slot = 0;
     auto stamp = [&]() { if (m.trace && tid == 0 && blockIdx.x < m.traceCtas) m.trace[(size_t)blockIdx.x * m.traceStride + slot] = globalTimerNs(); slot++; };
     stamp();
-    // embedding: CTA c copies its slice of the row
-    {
-        int tok = m.tokens[0];
-        if (tok < 0 || (uint32_t)tok >= m.vocabFull) tok = 0;
-        const uint32_t per = (m.dim + gridDim.x - 1) / gridDim.x;
-        const uint32_t b = blockIdx.x * per, e = min(b + per, m.dim);
-        for (uint32_t i = b + tid; i < e; i += kConsumerThreads) m.x[i] = m.embedding[(size_t)tok * m.dim + i];
-    }
+    // Epochs of the LL vectors: launch sequence number (device resident, bumped by CTA 0 at the end of every launch) x 1024 +
+    // phase index. Phase indices: 0 = embedding; layer l: 1+5l QKV, 2+5l attention, 3+5l WO, 4+5l W1|W3, 5+5l W2.
+    const uint32_t seqBase = __ldcg(m.launchSeq) << 10;
     int p = m.pos[0];
     if (p < 0) p = 0;
     if ((uint32_t)p >= m.seqLen) p = m.seqLen - 1;
-    gridBarrier(m.gridCounter, barTarget, tid);
+    if (tid < HD) sm.rope[tid] = m.rope[(size_t)p * HD + tid];
+    // embedding: every CTA writes the rows of the residual stream it owns in the WO / W2 phases (same thread -> same rows, so
+    // the residual read-modify-write never depends on another CTA's store)
+    {
+        int tok = m.tokens[0];
+        if (tok < 0 || (uint32_t)tok >= m.vocabFull) tok = 0;
+        uint32_t pairBegin, tileRows;
+        megaTile(m.ph[MP_WO], pairBegin, tileRows);
+        if ((uint32_t)tid < tileRows) stW(m.xW + pairBegin * 2 + tid, m.embedding[(size_t)tok * m.dim + pairBegin * 2 + tid], seqBase);
+    }
+    gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
     auto prefetchVec = [&](const float *p) {   // norm weights are constants: pull them towards L2 ahead of their phase
         for (uint32_t i = (blockIdx.x * kConsumerThreads + tid) * 32; i < m.dim; i += gridDim.x * kConsumerThreads * 32)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i));
     };
     for (uint32_t l = 0; l < m.nLayers; l++) {
         const MegaLayer &L = m.layers[l];
+        const uint32_t e0 = seqBase + 5 * l;     // epoch of x entering the layer (embedding or previous W2)
         prefetchVec(L.norm1);
         prefetchVec(l + 1 < m.nLayers ? m.layers[l + 1].norm0 : m.finalNorm);
         stamp();
-        megaGemv<PRO_RMSNORM_, EPI_STORE_>(m, sm, m.ph[MP_QKV], m.x, L.norm0, m.qkv, 0, ring, tid, slot);
+        megaGemv<PRO_RMSNORM_, EPI_STORE_>(m, sm, m.ph[MP_QKV], m.xW, e0, L.norm0, m.qkvW, e0 + 1, nullptr, 0, ring, tid, slot);
         stamp();
-        gridBarrier(m.gridCounter, barTarget, tid);
+        gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
         stamp();
-        megaAttention<HD>(m, sm, L, p, tid);
+        megaAttention<HD>(m, sm, L, p, tid, e0 + 1, e0 + 2);
         stamp();
-        gridBarrier(m.gridCounter, barTarget, tid);
+        gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
         stamp();
-        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.ph[MP_WO], m.z, nullptr, m.x, 0, ring, tid, slot);
+        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.ph[MP_WO], m.zW, e0 + 2, nullptr, m.xW, e0 + 3, nullptr, 0, ring, tid, slot);
         stamp();
-        gridBarrier(m.gridCounter, barTarget, tid);
+        gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
         stamp();
-        megaGemv<PRO_RMSNORM_, EPI_SWIGLU_>(m, sm, m.ph[MP_W13], m.x, L.norm1, m.h, 0, ring, tid, slot);
+        megaGemv<PRO_RMSNORM_, EPI_SWIGLU_>(m, sm, m.ph[MP_W13], m.xW, e0 + 3, L.norm1, m.hW, e0 + 4, nullptr, 0, ring, tid, slot);
         stamp();
-        gridBarrier(m.gridCounter, barTarget, tid);
+        gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
         stamp();
-        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.ph[MP_W2], m.h, nullptr, m.x, 1, ring, tid, slot);
+        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.ph[MP_W2], m.hW, e0 + 4, nullptr, m.xW, e0 + 5, nullptr, 1, ring, tid, slot);
         stamp();
-        gridBarrier(m.gridCounter, barTarget, tid);
+        gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
     }
     stamp();
-    megaGemv<PRO_RMSNORM_, EPI_ARGMAX_>(m, sm, m.ph[MP_LOGITS], m.x, m.finalNorm, m.logits, 0, ring, tid, slot);
+    megaGemv<PRO_RMSNORM_, EPI_ARGMAX_>(m, sm, m.ph[MP_LOGITS], m.xW, seqBase + 5 * m.nLayers, m.finalNorm, nullptr, 0, m.logits, 0, ring, tid, slot);
     stamp();
+    // every CTA has read launchSeq long ago (before its first barrier arrival): CTA 0 may advance it for the next launch
+    if (blockIdx.x == 0 && tid == 0) *m.launchSeq = __ldcg(m.launchSeq) + 1u;
 }
 
 // Host: geometry + launch. Returns 1 if the model shape cannot use the persistent kernel.
@@ -656,7 +763,8 @@ int launchMegaDecode(MegaArgs m, int numSms, cudaStream_t stream) {
         if (n % 128) return 1;
         if (n > maxN) maxN = n;
     }
-    if (maxN > 8 * kConsumerThreads * 4 || m.dim > 4 * kConsumerThreads * 4) return 1;   // activation (+ norm) vectors live in registers during the prologue
+    if (m.dim > 4 * kConsumerThreads * 4) return 1;   // RMS-norm phases keep the dim-long vector (+ norm weights) in registers
+    if (5 * m.nLayers + 2 > 1023) return 1;           // phase index field of the LL epochs
     const uint32_t grid = (uint32_t)numSms;
     m.act = gHiddenAct;
     if (m.vocabLimit == 0) m.vocabLimit = 0xffffffffu;
@@ -672,7 +780,7 @@ int launchMegaDecode(MegaArgs m, int numSms, cudaStream_t stream) {
     }
     m.partialFloats = (partial + 3) / 4 * 4;
     m.planeBlocks = maxN / 32;
-    const size_t fixedBytes = (size_t)m.planeBlocks * (16 + 16 + 4 + 4) + (size_t)m.partialFloats * 4 + 32 * 4 + 2 * kMaxStages * 8 + 256;
+    const size_t fixedBytes = (size_t)m.planeBlocks * (16 + 16 + 4 + 4) + (size_t)m.partialFloats * 4 + 32 * 4 + 128 * 4 + 2 * kMaxStages * 8 + 256;
     const size_t budget = 226 * 1024;
     // stage must hold >= 4 rows of the widest matrix
     const uint32_t maxRowBytes = (maxN / 32) * 18;
@@ -699,18 +807,40 @@ int launchMegaDecode(MegaArgs m, int numSms, cudaStream_t stream) {
         for (uint32_t sft = 0; sft < (uint32_t)kConsumerWarps; sft++)
             if (((sft * P.recipNseg) >> 16) != sft / P.nseg) return 1;
     }
+    // residual phases: thread r of a CTA owns row r of its tile
+    if (2 * (m.ph[MP_WO].pairsQ + 1) > (uint32_t)kConsumerThreads) return 1;
     const size_t smemBytes = fixedBytes + (size_t)stages * stageBytes;
-    static size_t configured[2] = {0, 0};
+    // The kernel spins on grid barriers: every CTA must be resident at the same time. A cooperative launch makes the driver
+    // verify that (and fail the launch instead of letting the barrier hang); the attribute cache is per device.
     const int v = m.headDim == 128 ? 1 : 0;
-    if (smemBytes > configured[v]) {
-        if (v) DL_CUDA_CHECK(cudaFuncSetAttribute(megaDecodeKernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-        else DL_CUDA_CHECK(cudaFuncSetAttribute(megaDecodeKernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-        configured[v] = smemBytes;
+    int dev = 0;
+    DL_CUDA_CHECK(cudaGetDevice(&dev));
+    static size_t configured[16][2] = {};
+    static int maxCoResident[16][2] = {};
+    const void *fn = v ? (const void *)megaDecodeKernel<128> : (const void *)megaDecodeKernel<64>;
+    const int d = dev & 15;
+    if (smemBytes > configured[d][v]) {
+        DL_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        configured[d][v] = smemBytes;
+        int perSm = 0, sms = 0;
+        DL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, kTmaThreads, smemBytes));
+        DL_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        maxCoResident[d][v] = perSm * sms;
     }
+    if ((int)grid > maxCoResident[d][v]) return 1;   // would not be co-resident: the caller takes the multi-kernel path
     DL_CUDA_CHECK(cudaMemsetAsync(m.gridCounter, 0, sizeof(unsigned int), stream));
-    if (v) megaDecodeKernel<128><<<grid, kTmaThreads, smemBytes, stream>>>(m);
-    else megaDecodeKernel<64><<<grid, kTmaThreads, smemBytes, stream>>>(m);
-    DL_CUDA_CHECK(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTmaThreads);
+    cfg.dynamicSmemBytes = smemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (v) DL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, megaDecodeKernel<128>, m));
+    else DL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, megaDecodeKernel<64>, m));
     return 0;
 }
 

@@ -81,6 +81,7 @@ class InferenceSession:
             eng.run_decode_step()
             self._pin_out.copy_(eng.tokens[:1], non_blocking=True)
             torch.cuda.current_stream().synchronize()
+            eng.check_abort()
             self.pos += 1
             return int(self._pin_out[0])
         lg = self.forward_logits(token)

@@ -109,6 +109,7 @@ class RootInference:
         self.eng.run_decode_step()
         self._pin_out.copy_(self.eng.tokens[:1], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        self.eng.check_abort()
         return int(self._pin_out[0])
 
     def decode_greedy(self, token: int, pos: int, n_steps: int) -> List[int]:

@@ -37,7 +37,7 @@ class GlobalPtrs(C.Structure):
 
 
 class CommPtrs(C.Structure):
-    _fields_ = [("nRanks", u32), ("rank", u32), ("maxCtas", u32), ("slotStride", u32), ("arena", vp * 8),
+    _fields_ = [("nRanks", u32), ("rank", u32), ("maxCtas", u32), ("slotStride", u32), ("arena", vp * 8), ("mcArena", vp),
                 ("slotsOff", u64), ("flagsOff", u64), ("candValOff", u64), ("candIdxOff", u64), ("candFlagOff", u64),
                 ("gatherOff", u64), ("prefillSlotsOff", u64), ("prefillSlotStride", u32)]
 
@@ -98,6 +98,8 @@ def lib() -> C.CDLL:
     L.dl_vmm_selftest_kernel.restype = i32
     L.dl_engine_set_trace.argtypes = [vp, vp, u32]
     L.dl_engine_set_trace.restype = i32
+    L.dl_engine_aborted.argtypes = [vp]
+    L.dl_engine_aborted.restype = i32
     L.dl_engine_set_trace_all.argtypes = [vp, i32]
     L.dl_engine_set_trace_all.restype = i32
     L.dl_engine_num_sms.argtypes = [vp]

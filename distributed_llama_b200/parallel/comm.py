@@ -148,6 +148,7 @@ class Communicator:
         L = self.layout
         arr = (C.c_void_p * 8)(*([C.c_void_p(p) for p in self.arena_ptrs] + [None] * (8 - len(self.arena_ptrs))))
         return cl.CommPtrs(nRanks=self.world_size, rank=self.rank, maxCtas=MAX_CTAS, slotStride=slot_stride, arena=arr,
+                           mcArena=C.c_void_p(self.mc_ptr) if self.mc_ptr else None,
                            slotsOff=L.slots_off, flagsOff=L.flags_off, candValOff=L.cand_val_off, candIdxOff=L.cand_idx_off,
                            candFlagOff=L.cand_flag_off, gatherOff=L.gather_off, prefillSlotsOff=L.prefill_slots_off,
                            prefillSlotStride=L.prefill_slot_stride)

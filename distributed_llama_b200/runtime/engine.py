@@ -149,6 +149,12 @@ class Engine:
         cl.check(self._lib.dl_engine_set_vocab_limit(self._h, int(limit)), "engine_set_vocab_limit")
         self._graph_ready = False
 
+    def check_abort(self):
+        """Raises if a device-side wait loop ran out of its spin budget (a peer rank died or a CTA never became resident): the
+        kernels drain instead of hanging and flag the step as invalid (csrc/cuda/mega_decode.cu: SpinGuard)."""
+        if self._lib.dl_engine_aborted(self._h):
+            raise RuntimeError("device-side wait timed out: a tensor-parallel peer stopped responding (or the persistent kernel was not co-resident)")
+
     def enable_mega(self, enable: bool = True):
         """Single-token forwards through the persistent per-token kernel (dense models). Re-captures the decode graph."""
         cl.check(self._lib.dl_engine_enable_mega(self._h, 1 if enable else 0), "engine_enable_mega")
@@ -317,4 +323,5 @@ class Engine:
             for _ in range(n_steps):
                 cl.check(self._lib.dl_engine_forward(self._h, 1, 1, 1, cl.stream_ptr()), "engine_forward")
         out = self.history[start_pos + 1: start_pos + 1 + n_steps].cpu()
+        self.check_abort()
         return out.tolist()
