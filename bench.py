@@ -14,6 +14,7 @@ far larger than L2 (126 MB) so every step streams them from HBM — no L2 flush 
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import re
@@ -140,6 +141,7 @@ def run_ours(args):
     eng = sess.engine
     if args.decode_path == "multi":
         eng.enable_mega(False)
+    load_s = time.time() - t0
     log(f"[bench] rank {rank}: weights on device in {time.time() - t0:.1f}s ({sess.weights.bytes_uploaded / 1e9:.2f} GB uploaded)")
 
     steps, warmup = args.steps, max(args.warmup, 3)
@@ -186,23 +188,36 @@ def run_ours(args):
     barrier()
     dev_ms = max_over_ranks(s.elapsed_time(e))
     # ---- end-to-end through the public API: per step H2D(token,pos) from pinned memory + D2H(token) ----
-    sess.pos = pos0
-    tok = prompt[-1]
-    for _ in range(warmup):
-        tok = sess.next_token(tok)
-    sess.pos = pos0
-    tok = prompt[-1]
+    # 1 GPU: InferenceSession.next_token. N GPUs: the product path of `dllama inference --gpus N` — the root sends one control packet
+    # per token through the shared-memory channel (apps/runtime.py RootInference.forward_greedy), the workers mirror it in
+    # worker_loop; the root copies the sampled token back to pinned host memory every step.
+    from distributed_llama_b200.apps.runtime import RootInference, open_control_channel, worker_loop
+    chan = open_control_channel(comm) if world > 1 else None
+    e2e_tokens, e2e_ms = [], 0.0
+    if world > 1 and rank != 0:
+        worker_loop(sess, comm, chan)
+    else:
+        inf = RootInference(sess, comm, chan) if world > 1 else None
+
+        def one(tok_, pos_):
+            if inf is not None:
+                return inf.forward_greedy(tok_, pos_)
+            sess.pos = pos_
+            return sess.next_token(tok_)
+        tok, pos = prompt[-1], pos0
+        for _ in range(warmup):
+            tok = one(tok, pos); pos += 1
+        tok, pos = prompt[-1], pos0
+        torch.cuda.synchronize()
+        t_start = time.perf_counter()
+        for _ in range(steps):
+            tok = one(tok, pos); pos += 1
+            e2e_tokens.append(tok)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t_start) * 1e3      # root wall clock: every step ends with the token in host memory
+        if inf is not None:
+            inf.finish()
     barrier()
-    t_start = time.perf_counter()
-    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s2.record()
-    e2e_tokens = []
-    for _ in range(steps):
-        tok = sess.next_token(tok)
-        e2e_tokens.append(tok)
-    e2.record()
-    barrier()
-    e2e_ms = max_over_ranks(max(s2.elapsed_time(e2), (time.perf_counter() - t_start) * 1e3 if world == 1 else 0.0))
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -235,6 +250,8 @@ def run_ours(args):
             "hbm_roofline": {"weight_bytes_per_step_per_gpu": weight_bytes, "achieved_gbs": round(weight_bytes / ms_per_step / 1e6, 1),
                              "frac_of_measured_hbm": round(weight_bytes / ms_per_step / 1e6 / hbm, 3)},
             "clocks": clocks, "tokens_agree": e2e_tokens == toks, "impl": "ours",
+            "tokens_sha": hashlib.sha1(",".join(map(str, toks[:16])).encode()).hexdigest()[:16],   # first 16 greedy tokens: TP=N must equal TP=1
+            "load_s": round(load_s, 2), "bytes_uploaded_per_rank": int(sess.weights.bytes_uploaded),
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -34,6 +34,7 @@ struct Engine {
     uint2 *megaX = nullptr, *megaQkv = nullptr, *megaZ = nullptr, *megaH = nullptr;   // LL vectors of the persistent kernel
     unsigned int *megaSeq = nullptr;
     unsigned int *abortHost = nullptr, *abortDev = nullptr;   // mapped pinned word: device wait loops report a blown spin budget here
+    uint32_t megaInflight = 2;         // DL_MEGA_INFLIGHT: producer pacing of the persistent kernel (0 = unpaced)
     uint32_t megaCtas = 0;             // DL_MEGA_CTAS: grid size override of the persistent kernel (0 = one CTA per SM)
     bool useMega = false;
     uint32_t vocabLimit = 0;     // 0 = none; otherwise the greedy arg-max ignores vocabulary rows >= vocabLimit
@@ -111,7 +112,7 @@ static int engineDecodeMega(Engine &e, bool greedyAdvance, cudaStream_t stream) 
     m.embedding = e.g.embedding; m.finalNorm = e.g.finalNorm; m.rope = e.g.rope;
     m.wclsQs = (const uint8_t *)e.g.wclsQs; m.wclsSc = (const uint8_t *)e.g.wclsSc;
     m.tokens = e.g.tokens; m.pos = e.g.pos; m.history = e.g.history;
-    m.logits = e.g.logits;
+    m.logits = e.g.logits; m.maxInflight = e.megaInflight;
     m.xW = e.megaX; m.qkvW = e.megaQkv; m.zW = e.megaZ; m.hW = e.megaH; m.launchSeq = e.megaSeq; m.abortFlag = e.abortDev;
     m.attnPartial = e.g.attnPartial; m.attnCounters = e.g.attnCounters;
     m.argVal = e.g.argVal; m.argIdx = e.g.argIdx; m.argCounter = e.g.argCounter; m.gridCounter = e.megaCounter;
@@ -371,6 +372,7 @@ DL_EXPORT int dl_engine_enable_mega(void *h, int enable) {
             DL_CUDA_CHECK(cudaHostGetDevicePointer((void **)&e->abortDev, e->abortHost, 0));
         }
         if (const char *g = std::getenv("DL_MEGA_CTAS")) e->megaCtas = (uint32_t)std::atoi(g);
+        if (const char *g = std::getenv("DL_MEGA_INFLIGHT")) e->megaInflight = (uint32_t)std::atoi(g);
     }
     e->useMega = enable != 0;
     return 0;

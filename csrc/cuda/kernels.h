@@ -168,6 +168,7 @@ struct MegaArgs {
     unsigned int *argCounter;
     unsigned int *gridCounter;   // zeroed by a memset node before every launch
     uint32_t stageBytes, nStages, planeBlocks, partialFloats;   // shared-memory geometry (host computed)
+    uint32_t maxInflight;        // producer pacing: bulk-copy fills outstanding per CTA (0 = the whole ring)
     MegaPhase ph[5];
     uint32_t rowOffsetGlobal;
     uint32_t greedyAdvance;      // 1: publish the arg-max token and advance the position on the device

@@ -663,6 +663,13 @@ __global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_
             const uint64_t policy = policyEvictFirst();
             RingPos pr{0u, 0u};
             bool wrapped = false;   // every stage has been filled once: from now on wait for the consumers to free it
+            // Pacing: at most `maxInflight` fills are outstanding at any time. The ring (capacity) still runs up to nStages
+            // fills ahead of the consumers, but a freshly drained ring is refilled by a short pipeline of requests instead of
+            // one 180 KB burst per SM: 26 MB of queued bulk reads chip-wide put ~1-4 us of queueing delay in front of every
+            // latency-critical load (barrier polls, activation vectors) at the L2 slices (profiles/barrier_microbench.txt).
+            RingPos landed{0u, 0u};
+            uint32_t nIssued = 0, nLanded = 0;
+            const uint32_t maxInflight = m.maxInflight ? m.maxInflight : m.nStages;
             auto stream = [&](const uint8_t *qs, const uint8_t *sc, const MegaPhase &P) {
                 const uint32_t rowQsBytes = P.nblk * 16, rowScBytes = P.nblk * 2;
                 uint32_t pairBegin, tileRows;
@@ -671,6 +678,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_
                 for (uint32_t r0 = 0; r0 < tileRows; r0 += SR) {
                     const uint32_t st = pr.st;
                     if (wrapped) mbarWait(&sm.emptyBar[st], pr.par ^ 1u);
+                    while (nIssued - nLanded >= maxInflight) {
+                        mbarWait(&sm.fullBar[landed.st], landed.par);
+                        landed.advance(m.nStages);
+                        nLanded++;
+                    }
+                    nIssued++;
                     const uint32_t rows = min(SR, tileRows - r0);
                     const uint32_t bq = rows * rowQsBytes, bs = rows * rowScBytes;
                     uint8_t *dst = sm.ring + st * m.stageBytes;

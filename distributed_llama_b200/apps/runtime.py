@@ -79,6 +79,7 @@ class RootInference:
         self.eval_ms = 0.0
         self._ctl = torch.zeros(4, dtype=torch.int64, device=sess.device) if (comm is not None and chan is None) else None
         self._pin_out = torch.zeros(1, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
+        self._pin_in = torch.zeros(2, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
 
     def _send(self, op: int, pos: int, tokens: Sequence[int]):
         if self.comm is None:
@@ -105,7 +106,10 @@ class RootInference:
 
     def forward_greedy(self, token: int, pos: int) -> int:
         self._send(OP_STEP_GREEDY, pos, [token])
-        self.eng._set_inputs([token], pos)
+        # the root synchronises every step, so one pinned staging slot is enough (workers enqueue ahead: pageable staging)
+        self._pin_in[0], self._pin_in[1] = token, pos
+        self.eng.tokens[:1].copy_(self._pin_in[:1], non_blocking=True)
+        self.eng.pos[:1].copy_(self._pin_in[1:2], non_blocking=True)
         self.eng.run_decode_step()
         self._pin_out.copy_(self.eng.tokens[:1], non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -87,6 +87,16 @@ class _Uploader:
         self.bytes += t.numel()
         return t.to(self.device, non_blocking=False)
 
+    def cols(self, entry, first_col_byte: int, n_col_bytes: int) -> torch.Tensor:
+        """Uploads the byte columns [first_col_byte, +n_col_bytes) of every row of a tensor: the column slice of one rank is
+        gathered on the host (strided view of the mapped file) so only the bytes the rank owns cross PCIe — the reference's
+        splitColMatmulWeight does the same cut before streaming a slice to a worker (src/nn/nn-core.cpp:307-322)."""
+        row_bytes = quants.tensor_bytes(entry.type, entry.n)
+        view = self.mf.data[entry.offset: entry.offset + entry.d * row_bytes].reshape(entry.d, row_bytes)[:, first_col_byte:first_col_byte + n_col_bytes]
+        t = torch.from_numpy(np.ascontiguousarray(view))
+        self.bytes += t.numel()
+        return t.to(self.device, non_blocking=False)
+
     def f32(self, entry) -> torch.Tensor:
         x = self.mf.tensor_f32(entry)
         self.bytes += x.nbytes
@@ -186,10 +196,12 @@ def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="
 
     def col_sliced(name, layer, expert, dst: DeviceQ40, cols_local, dst_off=0, slice_rank=None):
         e = mf.entry(name, layer, expert)
-        raw = up.rows(e, 0, e.d)
-        repack_q40(raw, e.d, cols_local, dst, src_row_pitch=quants.tensor_bytes(e.type, e.n),
-                   src_col_byte_offset=quants.tensor_bytes(e.type, (rank if slice_rank is None else slice_rank) * cols_local),
-                   dst_row_offset=dst_off)
+        cbytes = quants.tensor_bytes(e.type, cols_local)
+        if cbytes == quants.tensor_bytes(e.type, e.n):
+            raw = up.rows(e, 0, e.d)
+        else:
+            raw = up.cols(e, (rank if slice_rank is None else slice_rank) * cbytes, cbytes)
+        repack_q40(raw, e.d, cols_local, dst, src_row_pitch=cbytes, src_col_byte_offset=0, dst_row_offset=dst_off)
 
     W = DeviceWeights(header=h, rank=rank, n_ranks=n_ranks, n_heads=nh, n_kv_heads=nkv, ff_dim=ff0, vocab=v0,
                       embedding=up.f32(mf.entry("embedding")), final_norm=up.f32(mf.entry("final_norm")),
