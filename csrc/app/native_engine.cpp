@@ -273,7 +273,7 @@ void NativeEngine::forward(uint32_t n, int logitsMode, bool greedyAdvance) {
 
 void NativeEngine::prefill(const std::vector<int32_t> &tokens, uint32_t pos) {
     if (pos + tokens.size() > seqLen_) throw std::runtime_error("position beyond the context length");
-    const bool tc = h_.nExperts == 0;
+    const bool tc = h_.nExperts == 0 || (h_.dim % 256 == 0 && h_.moeHiddenDim % 256 == 0);   // MoE: grouped tensor-core GEMMs need 256-wide K
     size_t i = 0;
     while (i < tokens.size()) {
         const size_t rem = tokens.size() - i;

@@ -113,7 +113,7 @@ static int engineDecodeMega(Engine &e, bool greedyAdvance, cudaStream_t stream) 
     m.wclsQs = (const uint8_t *)e.g.wclsQs; m.wclsSc = (const uint8_t *)e.g.wclsSc;
     m.tokens = e.g.tokens; m.pos = e.g.pos; m.history = e.g.history;
     m.logits = e.g.logits; m.maxInflight = e.megaInflight;
-    m.xW = e.megaX; m.qkvW = e.megaQkv; m.zW = e.megaZ; m.hW = e.megaH; m.launchSeq = e.megaSeq; m.abortFlag = e.abortDev;
+    m.xW = e.megaX; m.qkvW = e.megaQkv; m.zW = e.megaZ; m.hF = (float *)e.megaH; m.launchSeq = e.megaSeq; m.abortFlag = e.abortDev;
     m.attnPartial = e.g.attnPartial; m.attnCounters = e.g.attnCounters;
     m.argVal = e.g.argVal; m.argIdx = e.g.argIdx; m.argCounter = e.g.argCounter; m.gridCounter = e.megaCounter;
     m.rowOffsetGlobal = c.rank * c.vocab; m.greedyAdvance = greedyAdvance ? 1u : 0u; m.vocabLimit = e.vocabLimit;
@@ -238,7 +238,7 @@ static int enginePrefill(Engine &e, uint32_t T, uint32_t p0, int wantLogits, cud
     const bool pdl = false;   // plain stream order between the heterogeneous kernels of this path
     const uint32_t qDim = c.nHeads * c.headDim, kvDim = c.nKvHeads * c.headDim, qkvDim = qDim + 2 * kvDim;
     if (T < 1 || T > g.maxPrefill || T > 256) return -11;
-    if (c.wType != 0 || c.nExperts > 0) return -35;   // tensor-core path: dense-model q40 matrices
+    if (c.wType != 0) return -35;   // tensor-core path: q40 matrices
     const bool tp = e.comm.nRanks > 1;
     ArArgs arP{};
     if (tp) {
@@ -276,6 +276,17 @@ static int enginePrefill(Engine &e, uint32_t T, uint32_t p0, int wantLogits, cud
         }
         if (tp) { arP.parity = 0; DL_TRY(gemmQ40TcAr(L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, arP)); }
         else DL_TRY(gemmQ40Tc(GEPI_RESIDUAL_, L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, pdl));
+        if (c.nExperts > 0) {
+            // mixture of experts: route the whole chunk, sort the (token, expert) pairs, grouped tensor-core GEMMs, weighted combine
+            MoePrefillArgs mo{};
+            mo.x = g.px; mo.xnScratch = g.pxn; mo.norm = L.norm1; mo.gate = L.moeGate; mo.w13Qs = L.w13Qs; mo.w13Sc = L.w13Sc;
+            mo.w2Qs = L.w2Qs; mo.w2Sc = L.w2Sc; mo.T = T; mo.dim = c.dim; mo.ff = c.ffDim; mo.nExperts = c.nExperts; mo.k = c.nActiveExperts;
+            mo.firstLocal = c.moeFirstExpert; mo.nLocal = c.moeNumLocal; mo.eps = c.eps; mo.numSms = (int)c.numSms;
+            if (tp) { arP.parity = 1; mo.ar = arP; }
+            const int mr = moePrefillFfn(mo, stream);
+            if (mr != 0) return mr == 1 ? -36 : mr;
+            continue;
+        }
         DL_TRY(launchRmsNormBf16(g.px, c.dim, L.norm1, g.pxn, c.dim, c.dim, c.eps, T, stream));
         DL_TRY(gemmQ40Tc(GEPI_SWIGLU_BF16_, L.w13Qs, L.w13Sc, 2 * c.ffDim, c.dim, g.pxn, c.dim, T, g.phb, c.ffDim, c.numSms, stream, pdl));
         if (tp) { arP.parity = 1; DL_TRY(gemmQ40TcAr(L.w2Qs, L.w2Sc, c.dim, c.ffDim, g.phb, c.ffDim, T, g.px, c.dim, c.numSms, stream, arP)); }

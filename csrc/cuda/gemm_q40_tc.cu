@@ -45,6 +45,11 @@ struct GemmArgs {
     uint32_t rawStages;    // TMA-staged variant: depth of the raw q40 ring (2 or 3)
     uint32_t debugFlags;   // bit0: skip the proxy fence, bit1: skip the A-tile stores (timing experiments only)
     uint32_t act;          // gate activation of GEPI_SWIGLU_BF16 (gHiddenAct)
+    // Grouped (mixture-of-experts) mode, TMA-staged variant only: the weight matrix is nGroups stacked [grpRows][n] matrices, the
+    // activation / output rows are sorted by group; group g owns rows [grpOffset[g], grpOffset[g] + grpCount[g]) (device arrays
+    // written by moeSortKernel). Row tile t belongs to group t / grpTiles; groups without tokens are skipped by every warp role.
+    const int *grpCount, *grpOffset;
+    uint32_t grpTiles, grpRows, nGroups;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -314,11 +319,16 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
 
     const uint32_t nkb = a.n / kGmBlockK;
     const uint32_t nkq = (a.n + kGmRawK - 1) / kGmRawK;
-    const uint32_t nTilesM = (a.d + kGmBlockM - 1) / kGmBlockM;
+    const uint32_t nTilesM = a.grpCount ? a.nGroups * a.grpTiles : (a.d + kGmBlockM - 1) / kGmBlockM;
     const uint32_t splitK = a.splitK;
     const uint32_t nItems = nTilesM * splitK;
     // work item -> (row tile, K range in 256-wide raw chunks); consecutive items share a tile
     auto kqBegin = [&](uint32_t ks) { return (uint32_t)(((uint64_t)ks * nkq) / splitK); };
+    // grouped mode: (tile) -> weight row of the tile's first row, first activation/output row, number of valid tokens
+    const bool grouped = a.grpCount != nullptr;
+    auto tileRow0 = [&](uint32_t tile) { return grouped ? (tile / a.grpTiles) * a.grpRows + (tile % a.grpTiles) * kGmBlockM : tile * kGmBlockM; };
+    auto tileTokens = [&](uint32_t tile) { return grouped ? (uint32_t)__ldg(a.grpCount + tile / a.grpTiles) : a.T; };
+    auto tileTok0 = [&](uint32_t tile) { return grouped ? (uint32_t)__ldg(a.grpOffset + tile / a.grpTiles) : 0u; };
 
     pdlLaunchDependents();
     if (tid == 0) {
@@ -351,13 +361,15 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             uint32_t it = 0;
             for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
                 const uint32_t tile = item / splitK, ks = item - tile * splitK;
+                if (grouped && tileTokens(tile) == 0) continue;
+                const uint32_t wRow = tileRow0(tile);
                 for (uint32_t kq = kqBegin(ks); kq < kqBegin(ks + 1); kq++, it++) {
                     const uint32_t rs = it % a.rawStages, ph = (it / a.rawStages) & 1;
                     gmBarWait(&rawEmpty[rs], ph ^ 1);
                     uint8_t *dst = rawBase + (size_t)rs * kGmRawStageBytes;
                     gmBarExpectTx(&rawFull[rs], kGmRawStageBytes);
-                    tmaLoad2d(dst, &tmapQ, kq * 128, tile * kGmBlockM, &rawFull[rs]);                 // nibbles: 128 B per row
-                    tmaLoad2d(dst + kGmRawQsBytes, &tmapS, kq * 16, tile * kGmBlockM, &rawFull[rs]);   // scales: 16 B per row
+                    tmaLoad2d(dst, &tmapQ, kq * 128, wRow, &rawFull[rs]);                 // nibbles: 128 B per row
+                    tmaLoad2d(dst + kGmRawQsBytes, &tmapS, kq * 16, wRow, &rawFull[rs]);   // scales: 16 B per row
                 }
             }
         }
@@ -368,11 +380,13 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             uint32_t it = 0;
             for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
                 const uint32_t ks = item % splitK;
+                if (grouped && tileTokens(item / splitK) == 0) continue;
+                const uint32_t tok0 = tileTok0(item / splitK);
                 for (uint32_t kb = kqBegin(ks) * 4; kb < min(kqBegin(ks + 1) * 4, nkb); kb++, it++) {
                     const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
                     gmBarWait(&emptyBar[s], ph ^ 1);
                     gmBarExpectTx(&fullBar[s], bTileBytes);
-                    tmaLoad2d(smem + (size_t)s * stageBytes + kGmATileBytes, &tmapB, kb * kGmBlockK, 0, &fullBar[s]);
+                    tmaLoad2d(smem + (size_t)s * stageBytes + kGmATileBytes, &tmapB, kb * kGmBlockK, tok0, &fullBar[s]);
                 }
             }
         }
@@ -380,10 +394,12 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
         // ===================== MMA issuer =====================
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((nTile >> 3) << 17) | ((uint32_t)(kGmBlockM >> 4) << 24);
         uint32_t it = 0, tcount = 0;
-        for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x, tcount++) {
+        for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
             const uint32_t ks = item % splitK;
+            if (grouped && tileTokens(item / splitK) == 0) continue;
+            const uint32_t tc = tcount++;
             const uint32_t kb0 = kqBegin(ks) * 4, kb1 = min(kqBegin(ks + 1) * 4, nkb);
-            const uint32_t acc = tcount & 1, accPh = (tcount >> 1) & 1;
+            const uint32_t acc = tc & 1, accPh = (tc >> 1) & 1;
             gmBarWait(&tmemEmpty[acc], accPh ^ 1);
             tcFenceAfter();
             const uint32_t tmemD = tmemBase + acc * nTile;
@@ -408,13 +424,18 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
         pdlWait();   // the residual stream is read-modify-written
         const uint32_t q = warp - 4;
         uint32_t tcount = 0;
-        for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x, tcount++) {
+        for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
             const uint32_t tile = item / splitK, ks = item - tile * splitK;
-            const uint32_t acc = tcount & 1, accPh = (tcount >> 1) & 1;
+            const uint32_t Teff = tileTokens(tile);
+            if (grouped && Teff == 0) continue;
+            const uint32_t tc = tcount++;
+            const uint32_t acc = tc & 1, accPh = (tc >> 1) & 1;
             gmBarWait(&tmemFull[acc], accPh);
             tcFenceAfter();
-            const uint32_t f = tile * kGmBlockM + q * 32 + lane;
-            const bool fOk = f < a.d;
+            // grouped mode: f is the feature index inside the group's matrix, output rows start at the group's first sorted row
+            const uint32_t f = (grouped ? (tile % a.grpTiles) * kGmBlockM : tile * kGmBlockM) + q * 32 + lane;
+            const bool fOk = f < (grouped ? a.grpRows : a.d);
+            const uint32_t rowOff = tileTok0(tile);
             if (splitK > 1) {
                 // ---- split-K: park the partial accumulator, the last split of this 32-row quarter reduces in fixed order ----
                 float *mineS = a.splitScratch + (size_t)ks * a.T * a.d;
@@ -525,26 +546,28 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 continue;
             }
             for (uint32_t c0 = 0; c0 < nTile; c0 += 16) {
+                if (grouped && c0 >= Teff) break;   // warp-uniform: the remaining columns belong to other groups
                 uint32_t r[16];
                 float resid[16];
                 if (EPI == GEPI_RESIDUAL) {   // issue all residual loads of the 16-column group before any store (no serialised RMW chain)
 #pragma unroll
                     for (int j = 0; j < 16; j++)
-                        resid[j] = (c0 + j < a.T && fOk) ? __ldcg(reinterpret_cast<const float *>(a.out) + (size_t)(c0 + j) * a.outStride + f) : 0.f;
+                        resid[j] = (c0 + j < Teff && fOk) ? __ldcg(reinterpret_cast<const float *>(a.out) + (size_t)(rowOff + c0 + j) * a.outStride + f) : 0.f;
                 }
                 tmemLoad16(tmemBase + ((q * 32u) << 16) + acc * nTile + c0, r);
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     const uint32_t tok = c0 + j;
+                    const size_t orow = (size_t)(rowOff + tok) * a.outStride;
                     const float v = __uint_as_float(r[j]);
                     if (EPI == GEPI_SWIGLU_BF16) {
                         const float other = __shfl_xor_sync(0xffffffffu, v, 1);
-                        if (tok < a.T && fOk && !(lane & 1))
-                            reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(gateAct(v, a.act) * other);
-                    } else if (tok < a.T && fOk) {
-                        if (EPI == GEPI_STORE_F32) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v;
-                        if (EPI == GEPI_RESIDUAL) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v + resid[j];
-                        if (EPI == GEPI_STORE_BF16) reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + f] = __float2bfloat16_rn(v);
+                        if (tok < Teff && fOk && !(lane & 1))
+                            reinterpret_cast<__nv_bfloat16 *>(a.out)[orow + (f >> 1)] = __float2bfloat16_rn(gateAct(v, a.act) * other);
+                    } else if (tok < Teff && fOk) {
+                        if (EPI == GEPI_STORE_F32) reinterpret_cast<float *>(a.out)[orow + f] = v;
+                        if (EPI == GEPI_RESIDUAL) reinterpret_cast<float *>(a.out)[orow + f] = v + resid[j];
+                        if (EPI == GEPI_STORE_BF16) reinterpret_cast<__nv_bfloat16 *>(a.out)[orow + f] = __float2bfloat16_rn(v);
                     }
                 }
             }
@@ -563,6 +586,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
         uint32_t itR = 0;
         for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
             const uint32_t ks = item % splitK;
+            if (grouped && tileTokens(item / splitK) == 0) continue;
             for (uint32_t kq = kqBegin(ks); kq < kqBegin(ks + 1); kq++, itR++) {
                 const uint32_t rs = itR % a.rawStages, rph = (itR / a.rawStages) & 1;
                 gmBarWait(&rawFull[rs], rph);
@@ -764,6 +788,46 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
         case GEPI_RESIDUAL_AR:
             if (!tma || !ar) return -10;
             return launchGemm<GEPI_RESIDUAL_AR>(mapB, pq, ps, a, grid, smemBytes, stream, pdl);
+    }
+    return -5;
+}
+
+// Grouped GEMM for mixture-of-experts prefill: nGroups stacked [grpRows][n] q40 matrices (the experts of one layer), activation rows
+// sorted by expert. act: bf16 [rowsTotal][n]; grpCount / grpOffset: device arrays (moeSortKernel); maxTokens bounds the tokens of
+// one group (the prompt chunk length: a token visits an expert at most once). Output rows follow the sorted order.
+int gemmQ40TcGrouped(int epi, const void *qs, const void *scales, uint32_t nGroups, uint32_t grpRows, uint32_t n, const void *act,
+                     uint32_t actStride, uint32_t rowsTotal, uint32_t maxTokens, const int *grpCount, const int *grpOffset, void *out,
+                     uint32_t outStride, int numSms, cudaStream_t stream) {
+    if (maxTokens == 0 || maxTokens > 256 || n % 256 || grpRows % 2 || (epi != GEPI_STORE_F32 && epi != GEPI_SWIGLU_BF16 && epi != GEPI_STORE_BF16)) return 1;
+    EncodeTiledFn enc = encodeTiled();
+    if (!enc) return -2;
+    GemmArgs a{};
+    a.act = gHiddenAct;
+    a.qs = (const uint32_t *)qs; a.scales = (const __half *)scales; a.d = nGroups * grpRows; a.n = n; a.T = maxTokens;
+    a.nTile = (maxTokens + 15) / 16 * 16;
+    a.out = out; a.outStride = outStride;
+    a.grpCount = grpCount; a.grpOffset = grpOffset; a.grpRows = grpRows; a.grpTiles = (grpRows + kGmBlockM - 1) / kGmBlockM; a.nGroups = nGroups;
+    a.splitK = 1;
+    uint32_t cols = 32;
+    while (cols < 2 * a.nTile) cols *= 2;
+    a.tmemCols = cols;
+    const size_t stageBytes = kGmATileBytes + (size_t)a.nTile * 128;
+    const size_t budget = 227 * 1024 - 1024 - 512;
+    const uint32_t tryRaw[3] = {3, 3, 2}, tryStages[3] = {8, 4, 4};
+    for (int i = 0; i < 3 && !a.stages; i++)
+        if (tryStages[i] * stageBytes + (size_t)tryRaw[i] * kGmRawStageBytes <= budget) { a.stages = tryStages[i]; a.rawStages = tryRaw[i]; }
+    if (!a.stages) return 1;
+    const size_t smemBytes = a.stages * stageBytes + (size_t)a.rawStages * kGmRawStageBytes + 1024 + 512;
+    CUtensorMap mapB, mapQ, mapS;
+    if (!encode2d(enc, &mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, act, n, rowsTotal, (uint64_t)actStride * 2, kGmBlockK, a.nTile, CU_TENSOR_MAP_SWIZZLE_128B)) return -4;
+    if (!encode2d(enc, &mapQ, CU_TENSOR_MAP_DATA_TYPE_UINT8, qs, n / 2, a.d, n / 2, 128, kGmBlockM, CU_TENSOR_MAP_SWIZZLE_128B)) return -7;
+    if (!encode2d(enc, &mapS, CU_TENSOR_MAP_DATA_TYPE_UINT8, scales, n / 16, a.d, n / 16, 16, kGmBlockM, CU_TENSOR_MAP_SWIZZLE_NONE)) return -8;
+    const uint32_t nItems = nGroups * a.grpTiles;
+    const int grid = (int)(nItems < (uint32_t)numSms ? nItems : (uint32_t)numSms);
+    switch (epi) {
+        case GEPI_STORE_F32: return launchGemm<GEPI_STORE_F32>(mapB, &mapQ, &mapS, a, grid, smemBytes, stream, false);
+        case GEPI_SWIGLU_BF16: return launchGemm<GEPI_SWIGLU_BF16>(mapB, &mapQ, &mapS, a, grid, smemBytes, stream, false);
+        case GEPI_STORE_BF16: return launchGemm<GEPI_STORE_BF16>(mapB, &mapQ, &mapS, a, grid, smemBytes, stream, false);
     }
     return -5;
 }

@@ -158,7 +158,8 @@ struct MegaArgs {
     const uint8_t *wclsQs, *wclsSc;
     int *tokens, *pos, *history;
     float *logits;
-    uint2 *xW, *qkvW, *zW, *hW;  // phase-crossing vectors as LL words {f32, epoch} (engine-owned, see mega_decode.cu)
+    uint2 *xW, *qkvW, *zW;       // phase-crossing vectors as LL words {f32, epoch} (engine-owned, see mega_decode.cu)
+    float *hF;                   // SwiGLU vector: plain f32 behind a fenced barrier (too large to pay the 2x LL footprint)
     unsigned int *launchSeq;     // device-resident launch counter (epoch base)
     unsigned int *abortFlag;     // host-mapped: set by a wait loop that ran out of its spin budget
     float *attnPartial;
@@ -186,6 +187,21 @@ int gemmQ40Tc(int epi, const void *qs, const void *scales, uint32_t d, uint32_t 
               void *out, uint32_t outStride, int numSms, cudaStream_t stream, bool pdl);
 int gemmQ40TcAr(const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride, uint32_t T, void *out,
                 uint32_t outStride, int numSms, cudaStream_t stream, const ArArgs &ar);   // GEMM + fused all-reduce + residual
+int gemmQ40TcGrouped(int epi, const void *qs, const void *scales, uint32_t nGroups, uint32_t grpRows, uint32_t n, const void *act,
+                     uint32_t actStride, uint32_t rowsTotal, uint32_t maxTokens, const int *grpCount, const int *grpOffset, void *out,
+                     uint32_t outStride, int numSms, cudaStream_t stream);   // 1: shape not covered
+// Mixture-of-experts feed-forward over a prompt chunk (moe_prefill.cu)
+struct MoePrefillArgs {
+    float *x;                     // [T][dim] residual stream, updated in place
+    void *xnScratch;              // bf16 [T][dim]
+    const float *norm, *gate;     // ffn rms-norm weight [dim], router gate [nExperts][dim] f32
+    const void *w13Qs, *w13Sc, *w2Qs, *w2Sc;
+    uint32_t T, dim, ff, nExperts, k, firstLocal, nLocal;
+    float eps;
+    int numSms;
+    ArArgs ar;                    // nRanks > 1: partial sums are all-reduced over peer memory inside the combine kernel
+};
+int moePrefillFfn(const MoePrefillArgs &a, cudaStream_t stream);   // 1: shape not covered
 int launchRmsNormBf16(const float *x, uint32_t xStride, const float *w, void *y, uint32_t yStride, uint32_t n, float eps, uint32_t T,
                       cudaStream_t stream);
 

@@ -18,6 +18,8 @@
 //     NVSwitch multicast mapping reaches every rank; unicast peer stores when no multicast object exists) and the cross-rank
 //     arg-max.
 // The kernel takes over the roles of NnExecutor's step loop + barriers (reference src/nn/nn-executor.cpp:137-175) on the GPU.
+#include <type_traits>
+
 #include "kernels.h"
 #include "tma_common.cuh"
 
@@ -71,6 +73,22 @@ __device__ __forceinline__ void gridBarrier(unsigned int *ctr, unsigned int &tar
         SpinGuard g(abortFlag);
         do {
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target && !g.tick());
+    }
+    consumerBarrier();
+}
+
+// Fenced variant for the one boundary whose payload is too large for LL words (the 14336-long SwiGLU vector: as 8-byte words it
+// costs every CTA 114 KB of L2 reads per layer, more than the fence): release/acquire make the plain f32 stores visible.
+__device__ __forceinline__ void gridBarrierFenced(unsigned int *ctr, unsigned int &target, int tid, unsigned int *abortFlag) {
+    consumerBarrier();
+    if (tid == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        target += gridDim.x;
+        unsigned int v;
+        SpinGuard g(abortFlag);
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         } while (v < target && !g.tick());
     }
     consumerBarrier();
@@ -130,9 +148,11 @@ __device__ __forceinline__ void megaTile(const MegaPhase &P, uint32_t &pairBegin
 // One GEMV phase on the consumer warps.
 // `in` / inEpoch: LL vector consumed by the prologue; `outW` / outEpoch: LL vector produced by the epilogue (EPI_RESIDUAL: the
 // residual stream itself, read-modify-written on the rows this CTA owns); `outF`: plain f32 output of the logits phase.
-template <int PRO, int EPI>
+// IN_PLAIN: the input vector is plain f32 at `inF` (made visible by a fenced barrier) instead of LL words at `in`.
+template <int PRO, int EPI, bool IN_PLAIN = false>
 __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase &P, const uint2 *in, uint32_t inEpoch, const float *normW,
-                         uint2 *outW, uint32_t outEpoch, float *outF, uint32_t arParity, RingPos &ring, int tid, uint32_t &slot) {
+                         uint2 *outW, uint32_t outEpoch, float *outF, uint32_t arParity, RingPos &ring, int tid, uint32_t &slot,
+                         const float *inF = nullptr) {
     auto stamp = [&]() { if (m.trace && tid == 0 && blockIdx.x < m.traceCtas) m.trace[(size_t)blockIdx.x * m.traceStride + slot] = globalTimerNs(); slot++; };
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t n = P.n;
@@ -172,7 +192,8 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
 #pragma unroll
             for (int k = 0; k < kMaxVec; k++) {
                 const uint32_t i = vecBase + k * kConsumerThreads + tid;
-                xv[k] = i < nVec ? ldW4wait(in, i, inEpoch, m.abortFlag) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (IN_PLAIN) xv[k] = i < nVec ? __ldcg(reinterpret_cast<const float4 *>(inF) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                else xv[k] = i < nVec ? ldW4wait(in, i, inEpoch, m.abortFlag) : make_float4(0.f, 0.f, 0.f, 0.f);
                 ss += xv[k].x * xv[k].x + xv[k].y * xv[k].y + xv[k].z * xv[k].z + xv[k].w * xv[k].w;
             }
             float inv = 1.f;
@@ -303,7 +324,7 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
         return v;
     };
     if (EPI == EPI_SWIGLU_) {
-        for (uint32_t p = tid; p < tileRows / 2; p += kConsumerThreads) stW(outW + pairBegin + p, gateAct(rowSum(2 * p), m.act) * rowSum(2 * p + 1), outEpoch);
+        for (uint32_t p = tid; p < tileRows / 2; p += kConsumerThreads) outF[pairBegin + p] = gateAct(rowSum(2 * p), m.act) * rowSum(2 * p + 1);
     } else if (EPI == EPI_STORE_) {
         for (uint32_t r = tid; r < tileRows; r += kConsumerThreads) stW(outW + rowBase + r, rowSum(r), outEpoch);
     } else if (EPI == EPI_RESIDUAL_) {
@@ -470,15 +491,66 @@ __device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaL
         const uint32_t end = min(begin + chunk, nPos);
         const bool ownsNew = end == nPos;
         const uint32_t cachedEnd = ownsNew ? end - 1 : end;
-        float q[DPL];
+        __nv_bfloat16 *kHead = L.kCache + (size_t)kvh * m.seqLen * HD;
+        __nv_bfloat16 *vHead = L.vCache + (size_t)kvh * m.seqLen * HD;
+        const __nv_bfloat16 *kBase = kHead + lane * DPL;
+        const __nv_bfloat16 *vBase = vHead + lane * DPL;
+        constexpr int UN = 4;
+        using RawT = typename std::conditional<DPL == 4, uint2, uint32_t>::type;   // DPL bf16 values of one cache row
+        RawT kRaw[UN], vRaw[UN];
+        auto loadBatch = [&](uint32_t s0) {
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const uint32_t s = s0 + u;
+                if (s < cachedEnd) {
+                    kRaw[u] = *reinterpret_cast<const RawT *>(kBase + (size_t)s * HD);
+                    vRaw[u] = *reinterpret_cast<const RawT *>(vBase + (size_t)s * HD);
+                }
+            }
+        };
+        auto unpack = [&](const RawT &r, float (&o)[DPL]) {
+            if constexpr (DPL == 4) {
+                const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.x));
+                const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.y));
+                o[0] = a0.x; o[1] = a0.y; o[2] = a1.x; o[3] = a1.y;
+            } else {
+                const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r));
+                o[0] = a0.x; o[1] = a0.y;
+            }
+        };
+        // Everything that does not depend on this layer's q is requested first: the first batch of cached K/V rows (and, on the warp
+        // that owns the new position, the raw k/v words) are in flight while q is polled — one L2 round trip instead of three.
+        uint32_t s0 = begin + warp * UN;
+        loadBatch(s0);
+        const bool newRow = ownsNew && warp == 0;
+        const uint2 *ksrc = m.qkvW + qDim + (size_t)kvh * HD + lane * DPL;
+        const uint2 *vsrc = m.qkvW + qDim + kvDim + (size_t)kvh * HD + lane * DPL;
+        float q[DPL], kn[DPL], vn[DPL];
         {
             const uint2 *src = m.qkvW + (size_t)h * HD + lane * DPL;
             if constexpr (DPL == 4) {
+                uint4 ka0, ka1, va0, va1;
+                if (newRow) { ka0 = ldW2(ksrc); ka1 = ldW2(ksrc + 2); va0 = ldW2(vsrc); va1 = ldW2(vsrc + 2); }
                 const float4 v = ldW4wait(src, 0, inEpoch, m.abortFlag);
                 q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+                if (newRow) {
+                    if (ka0.y != inEpoch || ka0.w != inEpoch || ka1.y != inEpoch || ka1.w != inEpoch || va0.y != inEpoch || va0.w != inEpoch ||
+                        va1.y != inEpoch || va1.w != inEpoch) {
+                        const float4 a = ldW4wait(ksrc, 0, inEpoch, m.abortFlag), bq = ldW4wait(vsrc, 0, inEpoch, m.abortFlag);
+                        kn[0] = a.x; kn[1] = a.y; kn[2] = a.z; kn[3] = a.w;
+                        vn[0] = bq.x; vn[1] = bq.y; vn[2] = bq.z; vn[3] = bq.w;
+                    } else {
+                        kn[0] = __uint_as_float(ka0.x); kn[1] = __uint_as_float(ka0.z); kn[2] = __uint_as_float(ka1.x); kn[3] = __uint_as_float(ka1.z);
+                        vn[0] = __uint_as_float(va0.x); vn[1] = __uint_as_float(va0.z); vn[2] = __uint_as_float(va1.x); vn[3] = __uint_as_float(va1.z);
+                    }
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < DPL; i++) q[i] = ldWwait(src + i, inEpoch, m.abortFlag);
+                if (newRow) {
+#pragma unroll
+                    for (int i = 0; i < DPL; i++) { kn[i] = ldWwait(ksrc + i, inEpoch, m.abortFlag); vn[i] = ldWwait(vsrc + i, inEpoch, m.abortFlag); }
+                }
             }
         }
         normRope(q, L.qNorm);
@@ -488,22 +560,7 @@ __device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaL
         float mx = -INFINITY, l = 0.f, acc[DPL];
 #pragma unroll
         for (int i = 0; i < DPL; i++) acc[i] = 0.f;
-        __nv_bfloat16 *kHead = L.kCache + (size_t)kvh * m.seqLen * HD;
-        __nv_bfloat16 *vHead = L.vCache + (size_t)kvh * m.seqLen * HD;
-        if (ownsNew && warp == 0) {
-            float kn[DPL], vn[DPL];
-            {
-                const uint2 *ks = m.qkvW + qDim + (size_t)kvh * HD + lane * DPL;
-                const uint2 *vs = m.qkvW + qDim + kvDim + (size_t)kvh * HD + lane * DPL;
-                if constexpr (DPL == 4) {
-                    const float4 a = ldW4wait(ks, 0, inEpoch, m.abortFlag), b = ldW4wait(vs, 0, inEpoch, m.abortFlag);
-                    kn[0] = a.x; kn[1] = a.y; kn[2] = a.z; kn[3] = a.w;
-                    vn[0] = b.x; vn[1] = b.y; vn[2] = b.z; vn[3] = b.w;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < DPL; i++) { kn[i] = ldWwait(ks + i, inEpoch, m.abortFlag); vn[i] = ldWwait(vs + i, inEpoch, m.abortFlag); }
-                }
-            }
+        if (newRow) {
             normRope(kn, L.kNorm);
             __nv_bfloat162 kb[DPL / 2], vb[DPL / 2];
 #pragma unroll
@@ -528,37 +585,18 @@ __device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaL
 #pragma unroll
             for (int i = 0; i < DPL; i++) acc[i] = vn[i];
         }
-        const __nv_bfloat16 *kBase = kHead + lane * DPL;
-        const __nv_bfloat16 *vBase = vHead + lane * DPL;
-        constexpr int UN = 4;
-        for (uint32_t s0 = begin + warp * UN; s0 < cachedEnd; s0 += kConsumerWarps * UN) {
+        for (; s0 < cachedEnd; s0 += kConsumerWarps * UN) {
             float kf[UN][DPL], vf[UN][DPL];
 #pragma unroll
             for (int u = 0; u < UN; u++) {
-                const uint32_t s = s0 + u;
-                if (s < cachedEnd) {
-                    if constexpr (DPL == 4) {
-                        const uint2 kr = *reinterpret_cast<const uint2 *>(kBase + (size_t)s * HD);
-                        const uint2 vr = *reinterpret_cast<const uint2 *>(vBase + (size_t)s * HD);
-                        const float2 k0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&kr.x));
-                        const float2 k1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&kr.y));
-                        const float2 v0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&vr.x));
-                        const float2 v1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&vr.y));
-                        kf[u][0] = k0.x; kf[u][1] = k0.y; kf[u][2] = k1.x; kf[u][3] = k1.y;
-                        vf[u][0] = v0.x; vf[u][1] = v0.y; vf[u][2] = v1.x; vf[u][3] = v1.y;
-                    } else {
-                        const uint32_t kr = *reinterpret_cast<const uint32_t *>(kBase + (size_t)s * HD);
-                        const uint32_t vr = *reinterpret_cast<const uint32_t *>(vBase + (size_t)s * HD);
-                        const float2 k0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&kr));
-                        const float2 v0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&vr));
-                        kf[u][0] = k0.x; kf[u][1] = k0.y;
-                        vf[u][0] = v0.x; vf[u][1] = v0.y;
-                    }
-                } else {
+                if (s0 + u < cachedEnd) { unpack(kRaw[u], kf[u]); unpack(vRaw[u], vf[u]); }
+                else {
 #pragma unroll
                     for (int i = 0; i < DPL; i++) { kf[u][i] = 0.f; vf[u][i] = 0.f; }
                 }
             }
+            const uint32_t cur = s0;
+            if (s0 + kConsumerWarps * UN < cachedEnd) loadBatch(s0 + kConsumerWarps * UN);   // next batch in flight during the math
             float sc[UN];
 #pragma unroll
             for (int u = 0; u < UN; u++) {
@@ -569,7 +607,7 @@ __device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaL
             }
 #pragma unroll
             for (int u = 0; u < UN; u++) {
-                if (s0 + u < cachedEnd) {
+                if (cur + u < cachedEnd) {
                     const float mNew = fmaxf(mx, sc[u]);
                     const float corr = __expf(mx - mNew);
                     const float pr = __expf(sc[u] - mNew);
@@ -751,11 +789,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_
         stamp();
         gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
         stamp();
-        megaGemv<PRO_RMSNORM_, EPI_SWIGLU_>(m, sm, m.ph[MP_W13], m.xW, e0 + 3, L.norm1, m.hW, e0 + 4, nullptr, 0, ring, tid, slot);
+        megaGemv<PRO_RMSNORM_, EPI_SWIGLU_>(m, sm, m.ph[MP_W13], m.xW, e0 + 3, L.norm1, nullptr, 0, m.hF, 0, ring, tid, slot);
         stamp();
-        gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
+        gridBarrierFenced(m.gridCounter, barTarget, tid, m.abortFlag);
         stamp();
-        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.ph[MP_W2], m.hW, e0 + 4, nullptr, m.xW, e0 + 5, nullptr, 1, ring, tid, slot);
+        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_, true>(m, sm, m.ph[MP_W2], nullptr, 0, nullptr, m.xW, e0 + 5, nullptr, 1, ring, tid, slot, m.hF);
         stamp();
         gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
     }

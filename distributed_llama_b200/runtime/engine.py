@@ -210,7 +210,9 @@ class Engine:
         tp = self.comm is not None and self.comm.world_size > 1
         # tensor parallel: the fused GEMM + all-reduce kernel needs 256-wide K slices on every rank
         tp_ok = (not tp) or ((self.w.n_heads * hdr.head_dim) % 256 == 0 and self.w.ff_dim % 256 == 0 and hdr.dim % 256 == 0)
-        tc_path = tp_ok and hdr.n_experts == 0 and self.use_tc_prefill
+        # mixture of experts: the grouped tensor-core GEMMs need 256-wide K on both expert matrices
+        moe_ok = hdr.n_experts == 0 or (hdr.dim % 256 == 0 and self.w.ff_dim % 256 == 0 and os.environ.get("DL_NO_MOE_PREFILL") is None)
+        tc_path = tp_ok and moe_ok and self.use_tc_prefill
         i = 0
         while i < len(tokens):
             rem = len(tokens) - i
