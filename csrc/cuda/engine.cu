@@ -31,6 +31,8 @@ struct Engine {
     bool traceAllCtas = false;   // persistent kernel: every CTA records its phase stamps (skew analysis, tools/trace_mega.py --all)
     MegaLayer *megaLayers = nullptr;   // device copy of the per-layer pointer table for the persistent decode kernel
     unsigned int *megaCounter = nullptr;
+    uint2 *megaX2 = nullptr;
+    uint32_t megaFlags = 0;            // DL_MEGA_FLAGS (bit 0: barrier-free LL hand-off)
     uint2 *megaX = nullptr, *megaQkv = nullptr, *megaZ = nullptr, *megaH = nullptr;   // LL vectors of the persistent kernel
     unsigned int *megaSeq = nullptr;
     unsigned int *abortHost = nullptr, *abortDev = nullptr;   // mapped pinned word: device wait loops report a blown spin budget here
@@ -113,7 +115,7 @@ static int engineDecodeMega(Engine &e, bool greedyAdvance, cudaStream_t stream) 
     m.wclsQs = (const uint8_t *)e.g.wclsQs; m.wclsSc = (const uint8_t *)e.g.wclsSc;
     m.tokens = e.g.tokens; m.pos = e.g.pos; m.history = e.g.history;
     m.logits = e.g.logits; m.maxInflight = e.megaInflight;
-    m.xW = e.megaX; m.qkvW = e.megaQkv; m.zW = e.megaZ; m.hF = (float *)e.megaH; m.launchSeq = e.megaSeq; m.abortFlag = e.abortDev;
+    m.xW = e.megaX; m.xW2 = e.megaX2; m.flags = e.megaFlags; m.qkvW = e.megaQkv; m.zW = e.megaZ; m.hF = (float *)e.megaH; m.launchSeq = e.megaSeq; m.abortFlag = e.abortDev;
     m.attnPartial = e.g.attnPartial; m.attnCounters = e.g.attnCounters;
     m.argVal = e.g.argVal; m.argIdx = e.g.argIdx; m.argCounter = e.g.argCounter; m.gridCounter = e.megaCounter;
     m.rowOffsetGlobal = c.rank * c.vocab; m.greedyAdvance = greedyAdvance ? 1u : 0u; m.vocabLimit = e.vocabLimit;
@@ -331,7 +333,7 @@ DL_EXPORT void dl_engine_destroy(void *h) {
     if (e->captureStream) cudaStreamDestroy(e->captureStream);
     if (e->megaLayers) cudaFree(e->megaLayers);
     if (e->megaCounter) cudaFree(e->megaCounter);
-    for (void *q : {(void *)e->megaX, (void *)e->megaQkv, (void *)e->megaZ, (void *)e->megaH, (void *)e->megaSeq}) if (q) cudaFree(q);
+    for (void *q : {(void *)e->megaX, (void *)e->megaX2, (void *)e->megaQkv, (void *)e->megaZ, (void *)e->megaH, (void *)e->megaSeq}) if (q) cudaFree(q);
     if (e->abortHost) cudaFreeHost(e->abortHost);
     delete e;
 }
@@ -372,7 +374,7 @@ DL_EXPORT int dl_engine_enable_mega(void *h, int enable) {
             if (cudaMalloc(p, bytes) != cudaSuccess) return false;
             return cudaMemset(*p, 0, bytes) == cudaSuccess;
         };
-        if (!allocW(&e->megaX, c.dim) || !allocW(&e->megaQkv, qkvDim) || !allocW(&e->megaZ, qDim) || !allocW(&e->megaH, c.ffDim)) return -41;
+        if (!allocW(&e->megaX, c.dim) || !allocW(&e->megaX2, c.dim) || !allocW(&e->megaQkv, qkvDim) || !allocW(&e->megaZ, qDim) || !allocW(&e->megaH, c.ffDim)) return -41;
         DL_CUDA_CHECK(cudaMalloc(&e->megaSeq, 256));
         const unsigned int one = 1;
         DL_CUDA_CHECK(cudaMemset(e->megaSeq, 0, 256));
@@ -383,6 +385,7 @@ DL_EXPORT int dl_engine_enable_mega(void *h, int enable) {
             DL_CUDA_CHECK(cudaHostGetDevicePointer((void **)&e->abortDev, e->abortHost, 0));
         }
         if (const char *g = std::getenv("DL_MEGA_CTAS")) e->megaCtas = (uint32_t)std::atoi(g);
+        if (const char *g = std::getenv("DL_MEGA_FLAGS")) e->megaFlags = (uint32_t)std::atoi(g);
         if (const char *g = std::getenv("DL_MEGA_INFLIGHT")) e->megaInflight = (uint32_t)std::atoi(g);
     }
     e->useMega = enable != 0;

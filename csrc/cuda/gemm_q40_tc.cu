@@ -38,6 +38,7 @@ struct GemmArgs {
     void *out;
     uint32_t outStride;   // elements between tokens
     uint32_t stages, tmemCols;
+    uint32_t bStages;      // TMA-staged variant: depth of the activation-tile ring (decoupled from the A-tile ring)
     uint32_t splitK;       // TMA-staged variant: K is cut into splitK ranges handled by different CTAs (work item = tile x split)
     float *splitScratch;   // [splitK][T][d] f32 partial accumulators
     unsigned int *splitCounters;   // [nTilesM * 4], zero-initialised, self-resetting (one per 32-row quarter of a tile)
@@ -64,6 +65,16 @@ __device__ __forceinline__ void gmBarWait(uint64_t *b, uint32_t parity) {
         "{\n.reg .pred p;\nGM_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra GM_DONE;\nbra GM_WAIT;\nGM_DONE:\n}\n" ::"r"(sAddr(b)),
         "r"(parity)
         : "memory");
+}
+// Wait used by warps that idle for a whole tile (epilogue): back off between probes so the spinning warp does not take issue
+// slots from the dequantisation warps that share its scheduler.
+__device__ __forceinline__ void gmBarWaitIdle(uint64_t *b, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(sAddr(b)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
 }
 __device__ __forceinline__ void tmaLoad2d(void *dst, const CUtensorMap *map, uint32_t c0, uint32_t c1, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(sAddr(dst)),
@@ -307,11 +318,17 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nTile = a.nTile;
     const uint32_t bTileBytes = nTile * 128;
-    const uint32_t stageBytes = kGmATileBytes + bTileBytes;
-    uint8_t *rawBase = smem + (size_t)a.stages * stageBytes;          // [kGmRawStages][18 KB], 1024-aligned (stageBytes % 1024 == 0)
-    uint64_t *fullBar = reinterpret_cast<uint64_t *>(rawBase + (size_t)a.rawStages * kGmRawStageBytes);
-    uint64_t *emptyBar = fullBar + kGmMaxStages;
-    uint64_t *tmemFull = emptyBar + kGmMaxStages;
+    // Two independent rings: A tiles (dequantised weights, written by the dequant warps) and B tiles (activations, TMA). Round 1
+    // kept them in one stage; with 64+ tokens only 4 such stages fit, i.e. ONE A tile per dequant group, so every group had to
+    // wait for the MMA of its previous tile before converting the next (ncu: dequant warps 50 % in long-scoreboard waits, tensor
+    // pipe 10 %). Now the A ring is 8 deep (2 per group) whatever the token count.
+    uint8_t *bBase = smem + (size_t)a.stages * kGmATileBytes;
+    uint8_t *rawBase = bBase + (size_t)a.bStages * bTileBytes;        // [rawStages][18 KB], 1024-aligned (all tiles are multiples of 1 KB)
+    uint64_t *fullBar = reinterpret_cast<uint64_t *>(rawBase + (size_t)a.rawStages * kGmRawStageBytes);   // A tile converted
+    uint64_t *emptyBar = fullBar + kGmMaxStages;                                                            // A tile consumed
+    uint64_t *bFull = emptyBar + kGmMaxStages;
+    uint64_t *bEmpty = bFull + kGmMaxStages;
+    uint64_t *tmemFull = bEmpty + kGmMaxStages;
     uint64_t *tmemEmpty = tmemFull + 2;
     uint64_t *rawFull = tmemEmpty + 2;
     uint64_t *rawEmpty = rawFull + kGmRawStagesMax;
@@ -333,8 +350,12 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
     pdlLaunchDependents();
     if (tid == 0) {
         for (uint32_t s = 0; s < a.stages; s++) {
-            gmBarInit(&fullBar[s], 1 + 2);   // activation TMA + the two dequant warps that own this k-slice
+            gmBarInit(&fullBar[s], 2);       // the two dequant warps that own this k-slice
             gmBarInit(&emptyBar[s], 1);
+        }
+        for (uint32_t s = 0; s < a.bStages; s++) {
+            gmBarInit(&bFull[s], 1);
+            gmBarInit(&bEmpty[s], 1);
         }
         for (int i = 0; i < 2; i++) {
             gmBarInit(&tmemFull[i], 1);
@@ -383,10 +404,10 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 if (grouped && tileTokens(item / splitK) == 0) continue;
                 const uint32_t tok0 = tileTok0(item / splitK);
                 for (uint32_t kb = kqBegin(ks) * 4; kb < min(kqBegin(ks + 1) * 4, nkb); kb++, it++) {
-                    const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
-                    gmBarWait(&emptyBar[s], ph ^ 1);
-                    gmBarExpectTx(&fullBar[s], bTileBytes);
-                    tmaLoad2d(smem + (size_t)s * stageBytes + kGmATileBytes, &tmapB, kb * kGmBlockK, tok0, &fullBar[s]);
+                    const uint32_t s = it % a.bStages, ph = (it / a.bStages) & 1;
+                    gmBarWait(&bEmpty[s], ph ^ 1);
+                    gmBarExpectTx(&bFull[s], bTileBytes);
+                    tmaLoad2d(bBase + (size_t)s * bTileBytes, &tmapB, kb * kGmBlockK, tok0, &bFull[s]);
                 }
             }
         }
@@ -405,15 +426,17 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             const uint32_t tmemD = tmemBase + acc * nTile;
             for (uint32_t kb = kb0; kb < kb1; kb++, it++) {
                 const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                const uint32_t sb = it % a.bStages, phb = (it / a.bStages) & 1;
+                gmBarWait(&bFull[sb], phb);
                 gmBarWait(&fullBar[s], ph);
                 tcFenceAfter();
                 if (lane == 0) {
-                    const uint32_t aAddr = sAddr(smem + (size_t)s * stageBytes);
-                    const uint64_t descA = makeSmemDesc(aAddr);
-                    const uint64_t descB = makeSmemDesc(aAddr + kGmATileBytes);
+                    const uint64_t descA = makeSmemDesc(sAddr(smem + (size_t)s * kGmATileBytes));
+                    const uint64_t descB = makeSmemDesc(sAddr(bBase + (size_t)sb * bTileBytes));
 #pragma unroll
                     for (uint32_t k = 0; k < kGmBlockK / 16; k++) umma(tmemD, descA + 2 * k, descB + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     ummaCommit(&emptyBar[s]);
+                    ummaCommit(&bEmpty[sb]);
                     if (kb == kb1 - 1) ummaCommit(&tmemFull[acc]);
                 }
                 __syncwarp();
@@ -430,7 +453,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             if (grouped && Teff == 0) continue;
             const uint32_t tc = tcount++;
             const uint32_t acc = tc & 1, accPh = (tc >> 1) & 1;
-            gmBarWait(&tmemFull[acc], accPh);
+            gmBarWaitIdle(&tmemFull[acc], accPh);
             tcFenceAfter();
             // grouped mode: f is the feature index inside the group's matrix, output rows start at the group's first sorted row
             const uint32_t f = (grouped ? (tile % a.grpTiles) * kGmBlockM : tile * kGmBlockM) + q * 32 + lane;
@@ -603,10 +626,13 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                         sv[rr][b] = *reinterpret_cast<const uint16_t *>(rbase + kGmRawQsBytes + row * 16 + c8 * 2);
                     }
                 }
+                // the raw chunk now lives in registers: hand the stage back to the TMA producer before the (long) conversion
+                __syncwarp();
+                if (lane == 0) gmBarArrive(&rawEmpty[rs]);
                 const uint32_t itA = itR * 4 + grp;
                 const uint32_t s = itA % a.stages, ph = (itA / a.stages) & 1;
                 gmBarWait(&emptyBar[s], ph ^ 1);
-                uint8_t *aTile = smem + (size_t)s * stageBytes;
+                uint8_t *aTile = smem + (size_t)s * kGmATileBytes;
 #pragma unroll
                 for (int rr = 0; rr < 2; rr++) {
                     const uint32_t row = j + 64 * rr;
@@ -633,10 +659,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 }
                 if (!(a.debugFlags & 1u)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) {
-                    gmBarArrive(&fullBar[s]);
-                    gmBarArrive(&rawEmpty[rs]);
-                }
+                if (lane == 0) gmBarArrive(&fullBar[s]);
             }
         }
     }
@@ -700,6 +723,23 @@ static bool encode2d(EncodeTiledFn enc, CUtensorMap *map, CUtensorMapDataType ty
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Shared-memory geometry of the TMA-staged variant: A ring (multiple of 4: each dequant group always revisits its own stages),
+// B ring (>= 2 activation tiles), raw q40 ring. Returns the dynamic shared-memory size, 0 if nothing fits.
+static size_t tmaGeometry(GemmArgs &a) {
+    const size_t bTile = (size_t)a.nTile * 128;
+    const size_t budget = 227 * 1024 - 1024 - 512;
+    const uint32_t tryA[4] = {8, 8, 4, 4}, tryRaw[4] = {3, 2, 3, 2};
+    for (int i = 0; i < 4; i++) {
+        const size_t fixed = (size_t)tryA[i] * kGmATileBytes + (size_t)tryRaw[i] * kGmRawStageBytes;
+        if (fixed + 2 * bTile > budget) continue;
+        size_t nb = (budget - fixed) / bTile;
+        if (nb > (size_t)kGmMaxStages) nb = kGmMaxStages;
+        a.stages = tryA[i]; a.rawStages = tryRaw[i]; a.bStages = (uint32_t)nb;
+        return fixed + nb * bTile + 1024 + 512;
+    }
+    return 0;
+}
+
 // act: bf16 [T][n] row-major (row stride actStride elements). variant: 0 auto, 1 register-prefetch dequant, 2 TMA-staged raw weights.
 static float *gSplitScratch = nullptr;
 static unsigned int *gSplitCounters = nullptr;
@@ -726,17 +766,14 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
     const size_t budget = 227 * 1024 - 1024 - 512;
     size_t rawBytes = 0;
     uint32_t stages = 0;
+    size_t tmaSmem = 0;
     if (tma) {
-        // Each dequant group owns every 4th k-slice, so a pipeline stage must always be revisited by the same group
-        // (mbarrier parity waits only disambiguate adjacent phases): the stage count has to be a multiple of 4.
-        const uint32_t tryRaw[3] = {3, 3, 2}, tryStages[3] = {8, 4, 4};
-        for (int i = 0; i < 3 && !stages; i++)
-            if (tryStages[i] * stageBytes + (size_t)tryRaw[i] * kGmRawStageBytes <= budget) { stages = tryStages[i]; a.rawStages = tryRaw[i]; }
-        if (!stages) {
+        tmaSmem = tmaGeometry(a);
+        if (!tmaSmem) {
             if (variant == 2) return -9;
             tma = false;
         } else {
-            rawBytes = (size_t)a.rawStages * kGmRawStageBytes;
+            stages = a.stages;
         }
     }
     if (!tma) {
@@ -745,7 +782,7 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
         if (stages < 2) return -3;
     }
     a.stages = stages;
-    const size_t smemBytes = stages * stageBytes + rawBytes + 1024 + 512;
+    const size_t smemBytes = tma ? tmaSmem : stages * stageBytes + rawBytes + 1024 + 512;
 
     CUtensorMap mapB, mapQ, mapS;
     if (!encode2d(enc, &mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, act, n, T, (uint64_t)actStride * 2, kGmBlockK, a.nTile, CU_TENSOR_MAP_SWIZZLE_128B))
@@ -761,8 +798,8 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
         const uint32_t nkq = n / 256;
         uint32_t sk = (uint32_t)numSms / nTilesM;
         if (sk > 8) sk = 8;
-        if (nkq < 32) sk = 1;             // K < 8192 (qkv, wo): the GEMM is short, splitting only adds the scratch round trip
-        if (sk > nkq / 8) sk = nkq / 8;   // every split keeps >= 8 raw chunks (2048 of K): below that the scratch round trip costs more than it saves
+        if (sk > nkq / 4) sk = nkq / 4;   // every split keeps >= 4 raw chunks (1024 of K)
+        if (const char *f = getenv("DL_GEMM_SPLITK")) sk = (uint32_t)atoi(f) < 1 ? 1 : (uint32_t)atoi(f);
         if (sk >= 2) {
             const size_t need = (size_t)sk * T * d * sizeof(float);
             if (need > gSplitScratchBytes) {
@@ -811,13 +848,8 @@ int gemmQ40TcGrouped(int epi, const void *qs, const void *scales, uint32_t nGrou
     uint32_t cols = 32;
     while (cols < 2 * a.nTile) cols *= 2;
     a.tmemCols = cols;
-    const size_t stageBytes = kGmATileBytes + (size_t)a.nTile * 128;
-    const size_t budget = 227 * 1024 - 1024 - 512;
-    const uint32_t tryRaw[3] = {3, 3, 2}, tryStages[3] = {8, 4, 4};
-    for (int i = 0; i < 3 && !a.stages; i++)
-        if (tryStages[i] * stageBytes + (size_t)tryRaw[i] * kGmRawStageBytes <= budget) { a.stages = tryStages[i]; a.rawStages = tryRaw[i]; }
-    if (!a.stages) return 1;
-    const size_t smemBytes = a.stages * stageBytes + (size_t)a.rawStages * kGmRawStageBytes + 1024 + 512;
+    const size_t smemBytes = tmaGeometry(a);
+    if (!smemBytes) return 1;
     CUtensorMap mapB, mapQ, mapS;
     if (!encode2d(enc, &mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, act, n, rowsTotal, (uint64_t)actStride * 2, kGmBlockK, a.nTile, CU_TENSOR_MAP_SWIZZLE_128B)) return -4;
     if (!encode2d(enc, &mapQ, CU_TENSOR_MAP_DATA_TYPE_UINT8, qs, n / 2, a.d, n / 2, 128, kGmBlockM, CU_TENSOR_MAP_SWIZZLE_128B)) return -7;

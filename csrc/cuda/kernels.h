@@ -158,6 +158,8 @@ struct MegaArgs {
     const uint8_t *wclsQs, *wclsSc;
     int *tokens, *pos, *history;
     float *logits;
+    uint2 *xW2;                  // second residual buffer (barrier-free hand-off experiment, flags bit 0)
+    uint32_t flags;
     uint2 *xW, *qkvW, *zW;       // phase-crossing vectors as LL words {f32, epoch} (engine-owned, see mega_decode.cu)
     float *hF;                   // SwiGLU vector: plain f32 behind a fenced barrier (too large to pay the 2x LL footprint)
     unsigned int *launchSeq;     // device-resident launch counter (epoch base)

@@ -113,7 +113,7 @@ __device__ __forceinline__ float ldWwait(const uint2 *p, uint32_t epoch, unsigne
     uint2 v = ldW(p);
     if (v.y != epoch) {
         SpinGuard g(abortFlag);
-        do { v = ldW(p); } while (v.y != epoch && !g.tick());
+        do { __nanosleep(100); v = ldW(p); } while (v.y != epoch && !g.tick());
     }
     return __uint_as_float(v.x);
 }
@@ -123,7 +123,7 @@ __device__ __forceinline__ float4 ldW4wait(const uint2 *base, uint32_t i4, uint3
     uint4 a = ldW2(p), b = ldW2(p + 2);
     if (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch) {
         SpinGuard g(abortFlag);
-        do { a = ldW2(p); b = ldW2(p + 2); } while ((a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch) && !g.tick());
+        do { __nanosleep(100); a = ldW2(p); b = ldW2(p + 2); } while ((a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch) && !g.tick());
     }
     return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
 }
@@ -152,7 +152,7 @@ __device__ __forceinline__ void megaTile(const MegaPhase &P, uint32_t &pairBegin
 template <int PRO, int EPI, bool IN_PLAIN = false>
 __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase &P, const uint2 *in, uint32_t inEpoch, const float *normW,
                          uint2 *outW, uint32_t outEpoch, float *outF, uint32_t arParity, RingPos &ring, int tid, uint32_t &slot,
-                         const float *inF = nullptr) {
+                         const float *inF = nullptr, const uint2 *resW = nullptr) {
     auto stamp = [&]() { if (m.trace && tid == 0 && blockIdx.x < m.traceCtas) m.trace[(size_t)blockIdx.x * m.traceStride + slot] = globalTimerNs(); slot++; };
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t n = P.n;
@@ -168,7 +168,7 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
     // The residual of the rows this CTA owns is fetched now, so that its L2 round trip overlaps the prologue and the main loop
     // (own rows were written by this very thread in the previous residual phase / the embedding phase: no epoch check needed).
     float resid = 0.f;
-    if (EPI == EPI_RESIDUAL_ && (uint32_t)tid < tileRows) resid = __uint_as_float(ldW(outW + rowBase + tid).x);
+    if (EPI == EPI_RESIDUAL_ && (uint32_t)tid < tileRows) resid = __uint_as_float(ldW((resW ? resW : outW) + rowBase + tid).x);
 
     // ---- prologue: (rmsnorm) + q80 quantisation of the activation vector. RMS-norm phases (n = dim <= 8192) keep the whole
     // vector in registers for the reduction; plain phases stream it in chunks of 16384 elements (any n) ----
@@ -767,6 +767,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_
         if ((uint32_t)tid < tileRows) stW(m.xW + pairBegin * 2 + tid, m.embedding[(size_t)tok * m.dim + pairBegin * 2 + tid], seqBase);
     }
     gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
+    // Experimental (MegaArgs::flags bit 0): no counter barrier where the consumer polls LL words anyway; the polls back off with
+    // nanosleep. The residual stream alternates between two buffers so a fast CTA can never overwrite words a slow one still expects.
+    const bool noBar = (m.flags & 1u) != 0;
+    auto llBarrier = [&]() { if (!noBar) gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag); };
+    uint2 *xA = m.xW, *xB = noBar ? m.xW2 : m.xW;
     auto prefetchVec = [&](const float *p) {   // norm weights are constants: pull them towards L2 ahead of their phase
         for (uint32_t i = (blockIdx.x * kConsumerThreads + tid) * 32; i < m.dim; i += gridDim.x * kConsumerThreads * 32)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i));
@@ -777,28 +782,28 @@ __global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_
         prefetchVec(L.norm1);
         prefetchVec(l + 1 < m.nLayers ? m.layers[l + 1].norm0 : m.finalNorm);
         stamp();
-        megaGemv<PRO_RMSNORM_, EPI_STORE_>(m, sm, m.ph[MP_QKV], m.xW, e0, L.norm0, m.qkvW, e0 + 1, nullptr, 0, ring, tid, slot);
+        megaGemv<PRO_RMSNORM_, EPI_STORE_>(m, sm, m.ph[MP_QKV], xA, e0, L.norm0, m.qkvW, e0 + 1, nullptr, 0, ring, tid, slot);
         stamp();
-        gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
+        llBarrier();
         stamp();
         megaAttention<HD>(m, sm, L, p, tid, e0 + 1, e0 + 2);
         stamp();
-        gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
+        llBarrier();
         stamp();
-        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.ph[MP_WO], m.zW, e0 + 2, nullptr, m.xW, e0 + 3, nullptr, 0, ring, tid, slot);
+        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_>(m, sm, m.ph[MP_WO], m.zW, e0 + 2, nullptr, xB, e0 + 3, nullptr, 0, ring, tid, slot, nullptr, xA);
         stamp();
-        gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
+        llBarrier();
         stamp();
-        megaGemv<PRO_RMSNORM_, EPI_SWIGLU_>(m, sm, m.ph[MP_W13], m.xW, e0 + 3, L.norm1, nullptr, 0, m.hF, 0, ring, tid, slot);
+        megaGemv<PRO_RMSNORM_, EPI_SWIGLU_>(m, sm, m.ph[MP_W13], xB, e0 + 3, L.norm1, nullptr, 0, m.hF, 0, ring, tid, slot);
         stamp();
         gridBarrierFenced(m.gridCounter, barTarget, tid, m.abortFlag);
         stamp();
-        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_, true>(m, sm, m.ph[MP_W2], nullptr, 0, nullptr, m.xW, e0 + 5, nullptr, 1, ring, tid, slot, m.hF);
+        megaGemv<PRO_PLAIN_, EPI_RESIDUAL_, true>(m, sm, m.ph[MP_W2], nullptr, 0, nullptr, xA, e0 + 5, nullptr, 1, ring, tid, slot, m.hF, xB);
         stamp();
-        gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
+        llBarrier();
     }
     stamp();
-    megaGemv<PRO_RMSNORM_, EPI_ARGMAX_>(m, sm, m.ph[MP_LOGITS], m.xW, seqBase + 5 * m.nLayers, m.finalNorm, nullptr, 0, m.logits, 0, ring, tid, slot);
+    megaGemv<PRO_RMSNORM_, EPI_ARGMAX_>(m, sm, m.ph[MP_LOGITS], xA, seqBase + 5 * m.nLayers, m.finalNorm, nullptr, 0, m.logits, 0, ring, tid, slot);
     stamp();
     // every CTA has read launchSeq long ago (before its first barrier arrival): CTA 0 may advance it for the next launch
     if (blockIdx.x == 0 && tid == 0) *m.launchSeq = __ldcg(m.launchSeq) + 1u;
