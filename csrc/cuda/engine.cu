@@ -39,6 +39,12 @@ struct Engine {
     uint32_t megaInflight = 2;         // DL_MEGA_INFLIGHT: producer pacing of the persistent kernel (0 = unpaced)
     uint32_t megaCtas = 0;             // DL_MEGA_CTAS: grid size override of the persistent kernel (0 = one CTA per SM)
     bool useMega = false;
+    // device sampler state (sampler.cu)
+    unsigned long long *rngState = nullptr;
+    float *probScratch = nullptr;
+    unsigned int *gatherEpoch = nullptr, *gatherBlockCounter = nullptr;
+    float **gatherUcDev = nullptr;
+    unsigned int **flagUcDev = nullptr;
     uint32_t vocabLimit = 0;     // 0 = none; otherwise the greedy arg-max ignores vocabulary rows >= vocabLimit
     bool tcAttn = true;          // prefill attention on tcgen05 (DL_NO_TC_ATTN=1: per-token CUDA-core kernel)
     bool fusedAttn = true, fusedArgmax = true, useTma = true;   // debugging switches (DL_NO_FUSED_ATTN / DL_NO_FUSED_ARGMAX / DL_NO_TMA)
@@ -403,6 +409,59 @@ DL_EXPORT int dl_engine_set_vocab_limit(void *h, uint32_t limit) {
 DL_EXPORT int dl_engine_aborted(void *h) {
     Engine *e = (Engine *)h;
     return (e->abortHost && *e->abortHost) ? 1 : 0;
+}
+
+// Seeds the device-resident xorshift* generator (same stream of coins as the host Sampler for the same seed) and allocates the
+// sampler scratch. Under tensor parallelism every rank must call this with the same seed.
+DL_EXPORT int dl_engine_sampler_seed(void *h, unsigned long long seed) {
+    Engine *e = (Engine *)h;
+    const dl::EngineConfig &c = e->cfg;
+    if (!e->rngState) {
+        DL_CUDA_CHECK(cudaMalloc(&e->rngState, 64));
+        DL_CUDA_CHECK(cudaMalloc(&e->probScratch, ((size_t)c.vocab * (c.nRanks ? c.nRanks : 1) + 16) * sizeof(float)));
+        DL_CUDA_CHECK(cudaMalloc(&e->gatherEpoch, 64));
+        DL_CUDA_CHECK(cudaMemset(e->gatherEpoch, 0, 64));
+        DL_CUDA_CHECK(cudaMalloc(&e->gatherBlockCounter, 64));
+        DL_CUDA_CHECK(cudaMemset(e->gatherBlockCounter, 0, 64));
+        if (e->comm.nRanks > 1) {
+            float *g[dl::kApiMaxRanks] = {};
+            unsigned int *f[dl::kApiMaxRanks] = {};
+            for (uint32_t r = 0; r < e->comm.nRanks; r++) {
+                g[r] = (float *)((uint8_t *)e->comm.arena[r] + e->comm.gatherOff);
+                f[r] = (unsigned int *)((uint8_t *)e->comm.arena[r] + e->comm.flagsOff);
+            }
+            DL_CUDA_CHECK(cudaMalloc(&e->gatherUcDev, sizeof(g)));
+            DL_CUDA_CHECK(cudaMalloc(&e->flagUcDev, sizeof(f)));
+            DL_CUDA_CHECK(cudaMemcpy(e->gatherUcDev, g, sizeof(g), cudaMemcpyHostToDevice));
+            DL_CUDA_CHECK(cudaMemcpy(e->flagUcDev, f, sizeof(f), cudaMemcpyHostToDevice));
+        }
+    }
+    if (seed == 0) seed = 0x9E3779B97F4A7C15ull;   // xorshift state must not be zero
+    DL_CUDA_CHECK(cudaMemcpy(e->rngState, &seed, sizeof(seed), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Samples the next token from the logits of the last forward (logitsMode 1) on the device: tokens[0] <- sample, pos[0]++, history.
+// Tensor parallel: the vocabulary slices are first gathered into every rank's arena (peer / multicast stores, no NCCL); every rank
+// then draws the same token from its own copy of the generator.
+DL_EXPORT int dl_engine_sample(void *h, float temperature, float topp, cudaStream_t stream) {
+    Engine *e = (Engine *)h;
+    const dl::EngineConfig &c = e->cfg;
+    if (!e->rngState) return -50;
+    const uint32_t nR = e->comm.nRanks > 1 ? e->comm.nRanks : 1;
+    const uint32_t full = c.vocab * nR;
+    const uint32_t n = (e->vocabLimit && e->vocabLimit < full) ? e->vocabLimit : full;
+    if (nR == 1)
+        return dl::launchSample(e->g.logits, e->probScratch, n, temperature, topp, e->rngState, e->g.tokens, e->g.pos, e->g.history, c.seqLen,
+                                nullptr, nullptr, 1, stream);
+    uint8_t *mine = (uint8_t *)e->comm.arena[e->comm.rank];
+    float *gatherLocal = (float *)(mine + e->comm.gatherOff);
+    unsigned int *flagLocal = (unsigned int *)(mine + e->comm.flagsOff);
+    float *gatherMc = e->comm.mcArena ? (float *)((uint8_t *)e->comm.mcArena + e->comm.gatherOff) : nullptr;
+    unsigned int *flagMc = e->comm.mcArena ? (unsigned int *)((uint8_t *)e->comm.mcArena + e->comm.flagsOff) : nullptr;
+    DL_TRY(dl::launchLogitsGather(e->g.logits, c.vocab, c.rank, nR, gatherMc, e->gatherUcDev, flagMc, e->flagUcDev, e->gatherBlockCounter, stream));
+    return dl::launchSample(gatherLocal, e->probScratch, n, temperature, topp, e->rngState, e->g.tokens, e->g.pos, e->g.history, c.seqLen, flagLocal,
+                            e->gatherEpoch, nR, stream);
 }
 
 DL_EXPORT int dl_engine_set_comm(void *h, const dl::CommPtrs *p) {

@@ -84,6 +84,8 @@ int dl_engine_set_comm(void *h, const dl::CommPtrs *p);
 int dl_engine_enable_mega(void *h, int enable);
 int dl_engine_set_vocab_limit(void *h, uint32_t limit);   // greedy arg-max never returns ids >= limit (tokenizer vocabulary size)
 int dl_engine_aborted(void *h);
+int dl_engine_sampler_seed(void *h, unsigned long long seed);
+int dl_engine_sample(void *h, float temperature, float topp, cudaStream_t stream);   // after a forward with logitsMode 1
 int dl_engine_set_trace(void *h, uint64_t *buf, uint32_t capLaunches);
 int dl_engine_set_trace_all(void *h, int allCtas);
 uint32_t dl_engine_num_sms(void *h);

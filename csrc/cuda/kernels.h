@@ -136,6 +136,13 @@ int launchEmbedding(const float *table, const int *tokens, float *x, uint32_t di
 int launchArgmaxAdvance(const float *logits, uint32_t vocab, int *tokenOut, int *pos, int *history, uint32_t historyCap,
                         cudaStream_t stream, bool pdl);   // single rank only: the index is local to `logits`
 
+// Device-side temperature / top-p sampler and the logits gather that feeds it under tensor parallelism (sampler.cu)
+int launchSample(const float *logits, float *probs, uint32_t n, float temperature, float topp, unsigned long long *rng, int *tokenOut, int *pos,
+                 int *history, uint32_t historyCap, const unsigned int *gatherFlag, unsigned int *gatherEpoch, uint32_t nRanks,
+                 cudaStream_t stream);
+int launchLogitsGather(const float *local, uint32_t v0, uint32_t rank, uint32_t nRanks, float *gatherMc, float *const *gatherUcDev,
+                       unsigned int *flagMc, unsigned int *const *flagUcDev, unsigned int *blockCounter, cudaStream_t stream);
+
 // Persistent decode kernel (mega_decode.cu)
 struct MegaLayer {
     const uint8_t *qkvQs, *qkvSc, *woQs, *woSc, *w13Qs, *w13Sc, *w2Qs, *w2Sc;

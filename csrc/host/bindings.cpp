@@ -189,6 +189,8 @@ PYBIND11_MODULE(_host, m) {
         .def("set_temperature", &Sampler::setTemperature)
         .def("set_topp", &Sampler::setTopp)
         .def("set_seed", &Sampler::setSeed)
+        .def_property_readonly("seed", &Sampler::seed)
+        .def_property_readonly("seed_generation", &Sampler::seedGeneration)
         .def_property_readonly("temperature", &Sampler::temperature)
         .def_property_readonly("topp", &Sampler::topp)
         .def_property_readonly("vocab_size", &Sampler::vocabSize);

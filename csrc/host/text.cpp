@@ -268,7 +268,7 @@ void softmaxInPlace(float *x, size_t n) {
 }
 
 Sampler::Sampler(uint32_t vocabSize, float temperature, float topp, uint64_t seed)
-    : vocabSize_(vocabSize), temperature_(temperature), topp_(topp), rng_(seed) {}
+    : vocabSize_(vocabSize), temperature_(temperature), topp_(topp), rng_(seed), seed_(seed) {}
 
 int32_t Sampler::sample(float *logits) {
     const int n = (int)vocabSize_;

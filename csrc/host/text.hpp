@@ -74,7 +74,9 @@ public:
     float nextCoin() { return rng_.nextF32(); }
     void setTemperature(float t) { temperature_ = t; }
     void setTopp(float p) { topp_ = p; }
-    void setSeed(uint64_t s) { rng_.state = s; }
+    void setSeed(uint64_t s) { rng_.state = s; seed_ = s; seedGeneration_++; }
+    uint64_t seed() const { return seed_; }                       // last seed given (constructor or setSeed)
+    uint32_t seedGeneration() const { return seedGeneration_; }   // bumped by every setSeed: device-side generators re-seed on change
     float temperature() const { return temperature_; }
     float topp() const { return topp_; }
     uint32_t vocabSize() const { return vocabSize_; }
@@ -83,6 +85,8 @@ private:
     uint32_t vocabSize_;
     float temperature_, topp_;
     Rng rng_;
+    uint64_t seed_ = 0;
+    uint32_t seedGeneration_ = 0;
     std::vector<std::pair<float, int32_t>> candidates_;
 };
 

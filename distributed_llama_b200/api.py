@@ -52,6 +52,7 @@ class InferenceSession:
         if self.tokenizer and self.tokenizer.vocab_size < self.header.vocab_size:
             self.engine.set_vocab_limit(self.tokenizer.vocab_size)
         self.pos = 0
+        self._dev_seeded = None
         self._pin_in = torch.zeros(2, dtype=torch.int32).pin_memory()
         self._pin_out = torch.zeros(1, dtype=torch.int32).pin_memory()
 
@@ -79,6 +80,19 @@ class InferenceSession:
             eng.tokens[:1].copy_(self._pin_in[:1], non_blocking=True)
             eng.pos[:1].copy_(self._pin_in[1:2], non_blocking=True)
             eng.run_decode_step()
+            self._pin_out.copy_(eng.tokens[:1], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            eng.check_abort()
+            self.pos += 1
+            return int(self._pin_out[0])
+        eng = self.engine
+        if self.device.type == "cuda" and not getattr(eng, "_parts", False):
+            # temperature / top-p on the device (csrc/cuda/sampler.cu): only the sampled token crosses PCIe
+            gen = (self.sampler.seed, self.sampler.seed_generation)
+            if self._dev_seeded != gen:
+                eng.seed_sampler(self.sampler.seed)
+                self._dev_seeded = gen
+            eng.step_sampled(token, self.pos, self.sampler.temperature, self.sampler.topp)
             self._pin_out.copy_(eng.tokens[:1], non_blocking=True)
             torch.cuda.current_stream().synchronize()
             eng.check_abort()

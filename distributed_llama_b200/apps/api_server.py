@@ -164,10 +164,7 @@ class ApiServer:
         self.det.reset()
         greedy = smp.temperature == 0.0
         while pos < max_pred:
-            if greedy:
-                token = inf.forward_greedy(token, pos)
-            else:
-                token = smp.sample(inf.forward_logits(token, pos).float().cpu().numpy())
+            token = inf.next_token(token, pos, smp)
             piece = tok.decode(token)
             kind = self.det.append(token, piece)
             if piece:

@@ -60,11 +60,7 @@ def inference(ctx: AppContext) -> None:
     while pos < max_pos:
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        if greedy:
-            token = inf.forward_greedy(token, pos)
-        else:
-            logits = inf.forward_logits(token, pos)
-            token = ctx.sampler.sample(logits.float().cpu().numpy())
+        token = inf.next_token(token, pos, ctx.sampler)
         dt = (time.perf_counter() - t0) * 1000
         pred_ms += dt
         piece = tok.decode(token).decode("utf-8", errors="replace")
@@ -155,10 +151,7 @@ def chat(ctx: AppContext) -> None:
         if public:
             print(public.decode("utf-8", errors="replace"), end="")
         while pos < seq_len:
-            if greedy:
-                token = inf.forward_greedy(token, pos)
-            else:
-                token = ctx.sampler.sample(inf.forward_logits(token, pos).float().cpu().numpy())
+            token = inf.next_token(token, pos, ctx.sampler)
             piece = tok.decode(token)
             kind = det.append(token, piece)
             if kind in (H.NOT_EOS, H.EOS):

@@ -20,7 +20,7 @@ from .. import host
 from ..api import InferenceSession
 from .args import AppArgs
 
-OP_STOP, OP_PREFILL, OP_STEP_LOGITS, OP_STEP_GREEDY, OP_DECODE_N = 0, 1, 2, 3, 4
+OP_STOP, OP_PREFILL, OP_STEP_LOGITS, OP_STEP_GREEDY, OP_DECODE_N, OP_STEP_SAMPLE, OP_SEED = 0, 1, 2, 3, 4, 5, 6
 
 
 def world():
@@ -106,6 +106,10 @@ class RootInference:
 
     def forward_greedy(self, token: int, pos: int) -> int:
         self._send(OP_STEP_GREEDY, pos, [token])
+        if self._pin_in is None:          # no CUDA device (CPU-side protocol tests)
+            self.eng._set_inputs([token], pos)
+            self.eng.run_decode_step()
+            return int(self.eng.tokens[0])
         # the root synchronises every step, so one pinned staging slot is enough (workers enqueue ahead: pageable staging)
         self._pin_in[0], self._pin_in[1] = token, pos
         self.eng.tokens[:1].copy_(self._pin_in[:1], non_blocking=True)
@@ -115,6 +119,37 @@ class RootInference:
         torch.cuda.current_stream().synchronize()
         self.eng.check_abort()
         return int(self._pin_out[0])
+
+    # ---- sampling on the device: the logits never leave the GPUs (csrc/cuda/sampler.cu) ----
+    @property
+    def device_sampling(self) -> bool:
+        return torch.cuda.is_available() and not getattr(self.eng, "_parts", False) and os.environ.get("DL_HOST_SAMPLER") is None
+
+    def seed(self, seed: int) -> None:
+        self._send(OP_SEED, 0, [seed & 0x7FFFFFFF, (seed >> 31) & 0x7FFFFFFF, (seed >> 62) & 0x3])
+        self.eng.seed_sampler(seed)
+
+    def forward_sampled(self, token: int, pos: int, temperature: float, topp: float) -> int:
+        import struct
+        t_bits, p_bits = struct.unpack("<ii", struct.pack("<ff", temperature, topp))
+        self._send(OP_STEP_SAMPLE, pos, [token, t_bits, p_bits])
+        self.eng.step_sampled(token, pos, temperature, topp)
+        self._pin_out.copy_(self.eng.tokens[:1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.eng.check_abort()
+        return int(self._pin_out[0])
+
+    def next_token(self, token: int, pos: int, sampler) -> int:
+        """One generated token with the sampler's settings: greedy and temperature/top-p both run on the device; the host sampler
+        is only used with the library-collective (multi-node) mode or DL_HOST_SAMPLER=1."""
+        if sampler.temperature == 0.0:
+            return self.forward_greedy(token, pos)
+        if self.device_sampling:
+            if getattr(self, "_seeded", None) != (sampler.seed, sampler.seed_generation):
+                self.seed(sampler.seed)
+                self._seeded = (sampler.seed, sampler.seed_generation)
+            return self.forward_sampled(token, pos, sampler.temperature, sampler.topp)
+        return int(sampler.sample(self.forward_logits(token, pos).float().cpu().numpy()))
 
     def decode_greedy(self, token: int, pos: int, n_steps: int) -> List[int]:
         """n greedy steps with the token fed back on the device (no host round trip per step): one control packet for all."""
@@ -159,6 +194,12 @@ def worker_loop(sess: InferenceSession, comm, chan=None) -> None:
             eng.run_decode_step()
         elif op == OP_DECODE_N:
             eng.decode_greedy(toks[0], pos, toks[1])
+        elif op == OP_SEED:
+            eng.seed_sampler(toks[0] | (toks[1] << 31) | (toks[2] << 62))
+        elif op == OP_STEP_SAMPLE:
+            import struct
+            temperature, topp = struct.unpack("<ff", struct.pack("<ii", toks[1], toks[2]))
+            eng.step_sampled(toks[0], pos, temperature, topp)
 
 
 @dataclass

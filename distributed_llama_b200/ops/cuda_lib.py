@@ -98,6 +98,12 @@ def lib() -> C.CDLL:
     L.dl_vmm_selftest_kernel.restype = i32
     L.dl_engine_set_trace.argtypes = [vp, vp, u32]
     L.dl_engine_set_trace.restype = i32
+    L.dl_engine_sampler_seed.argtypes = [vp, C.c_uint64]
+    L.dl_engine_sampler_seed.restype = i32
+    L.dl_engine_sample.argtypes = [vp, f32, f32, vp]
+    L.dl_engine_sample.restype = i32
+    L.dl_sample_logits.argtypes = [vp, vp, u32, f32, f32, vp, vp, vp]
+    L.dl_sample_logits.restype = i32
     L.dl_engine_aborted.argtypes = [vp]
     L.dl_engine_aborted.restype = i32
     L.dl_engine_set_trace_all.argtypes = [vp, i32]

@@ -149,6 +149,21 @@ class Engine:
         cl.check(self._lib.dl_engine_set_vocab_limit(self._h, int(limit)), "engine_set_vocab_limit")
         self._graph_ready = False
 
+    # -- device-side sampling --
+    def seed_sampler(self, seed: int):
+        """Seeds the device-resident generator (same xorshift* stream as the host Sampler). Every rank must use the same seed."""
+        cl.check(self._lib.dl_engine_sampler_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF), "engine_sampler_seed")
+        self._sampler_ready = True
+
+    def step_sampled(self, token: int, pos: int, temperature: float, topp: float) -> None:
+        """Forward of one token + temperature/top-p sampling on the device (csrc/cuda/sampler.cu); the sampled token lands in
+        tokens[0] and history[pos + 1]. No logits leave the GPU; under tensor parallelism the vocabulary slices are exchanged
+        through peer memory and every rank draws the same token."""
+        if not getattr(self, "_sampler_ready", False):
+            raise RuntimeError("seed_sampler() must be called first")
+        self.forward_batch([token], pos, logits_mode=1)
+        cl.check(self._lib.dl_engine_sample(self._h, float(temperature), float(topp), cl.stream_ptr()), "engine_sample")
+
     def check_abort(self):
         """Raises if a device-side wait loop ran out of its spin budget (a peer rank died or a CTA never became resident): the
         kernels drain instead of hanging and flag the step as invalid (csrc/cuda/mega_decode.cu: SpinGuard)."""

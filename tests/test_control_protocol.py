@@ -37,17 +37,20 @@ class _FakeSession:
         self.header = None
 
 
-def _rank_main(rank, world, init_file, out_dir):
+def _rank_main(rank, world, init_file, out_dir, use_shm):
     dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
-    from distributed_llama_b200.apps.runtime import RootInference, worker_loop
+    from distributed_llama_b200.apps.runtime import RootInference, open_control_channel, worker_loop
 
     class _Comm:
         world_size = world
+        single_node = True
     _Comm.rank = rank
     log = []
     sess = _FakeSession(log)
+    chan = open_control_channel(_Comm()) if use_shm else None      # shared-memory packets (default) or torch.distributed broadcasts
+    assert (chan is not None) == use_shm
     if rank == 0:
-        inf = RootInference(sess, _Comm())
+        inf = RootInference(sess, _Comm(), chan)
         inf.prefill([5, 6, 7, 8, 9], 0)
         inf.prefill([], 5)                  # empty chunk: nothing is sent
         inf.forward_logits(11, 5)
@@ -55,16 +58,20 @@ def _rank_main(rank, world, init_file, out_dir):
         assert tok == 13
         inf.finish()
     else:
-        worker_loop(sess, _Comm())
+        worker_loop(sess, _Comm(), chan)
     with open(os.path.join(out_dir, f"log{rank}.json"), "w") as f:
         json.dump(log, f)
     dist.destroy_process_group()
 
 
-def test_worker_mirrors_root_forwards():
+import pytest
+
+
+@pytest.mark.parametrize("use_shm", [True, False])
+def test_worker_mirrors_root_forwards(use_shm):
     with tempfile.TemporaryDirectory() as d:
         init_file = os.path.join(d, "rendezvous")
-        mp.spawn(_rank_main, args=(2, init_file, d), nprocs=2, join=True)
+        mp.spawn(_rank_main, args=(2, init_file, d, use_shm), nprocs=2, join=True)
         root = json.load(open(os.path.join(d, "log0.json")))
         worker = json.load(open(os.path.join(d, "log1.json")))
     assert root == worker
