@@ -13,6 +13,7 @@
 // Tensor parallelism (K4, reference: gather of vocab slices to the root, src/llm.cpp:587-599): logitsGatherKernel pushes this
 // rank's vocabulary slice into every rank's gather buffer (one multimem.st per 16 bytes through the NVSwitch multicast mapping, or
 // unicast peer stores) and bumps an arrival counter on every rank; the sampler waits for nRanks arrivals. No NCCL on the step path.
+#include "../common/dl_expf.h"
 #include "kernels.h"
 
 namespace dl {
@@ -178,28 +179,28 @@ __global__ void __launch_bounds__(kSampThreads, 1) sampleKernel(SampleArgs a) {
         }
         __syncthreads();
     }
-    const float invT = 1.0f / a.temperature;
-    // softmax statistics
+    // softmax statistics (IEEE division / shared exp / integer normaliser: the host sampler computes the very same numbers)
     float m = -INFINITY;
-    for (uint32_t i = threadIdx.x; i < n; i += kSampThreads) m = fmaxf(m, a.logits[i] * invT);
+    for (uint32_t i = threadIdx.x; i < n; i += kSampThreads) m = fmaxf(m, __fdiv_rn(a.logits[i], a.temperature));
     m = blockMax(m, red);
     // per-thread sums over contiguous chunks (index order), combined by a fixed tree
     const uint32_t chunk = (n + kSampThreads - 1) / kSampThreads;
     const uint32_t lo = threadIdx.x * chunk, hi = min(lo + chunk, n);
-    float s = 0.f;
+    unsigned long long sFix = 0;
     for (uint32_t i = lo; i < hi; i++) {
-        const float e = expf(a.logits[i] * invT - m);
+        const float e = expNeg(__fsub_rn(__fdiv_rn(a.logits[i], a.temperature), m));
         a.probs[i] = e;
-        s += e;
+        sFix += toFix(e);
     }
-    const float S = blockSum(s, red);
-    const float inv = 1.0f / S;
+    unsigned long long sTotal = 0;
+    (void)blockExclusiveScan(sFix, scratch + 8, &sTotal);
+    const float inv = __fdiv_rn(1.0f, __fdiv_rn((float)sTotal, kFix));
     if (threadIdx.x == 0) {
         unsigned long long st = *a.rng;          // xorshift* (reference src/tokenizer.cpp:25-36)
         st ^= st >> 12; st ^= st << 25; st ^= st >> 27;
         *a.rng = st;
         const uint32_t u = (uint32_t)((st * 0x2545F4914F6CDD1Dull) >> 32);
-        sCoin = (float)(u >> 8) / 16777216.0f;
+        sCoin = (float)(u >> 8) * 5.9604644775390625e-8f;   // / 2^24, exact
         sInt[2] = (int)n - 1;
     }
     __syncthreads();
@@ -222,10 +223,10 @@ __global__ void __launch_bounds__(kSampThreads, 1) sampleKernel(SampleArgs a) {
         __syncthreads();
         token = sInt[2];
     } else {
-        const float cutoff = (1.0f - a.topp) / (float)(n - 1);
+        const float cutoff = __fdiv_rn(1.0f - a.topp, (float)(n - 1));
         const Found cut = radixFind(a, inv, cutoff, toFix(a.topp), hist, scratch, sInt);
         // r = coin * cumulative (the reference multiplies the float prefix sum)
-        const float cumulative = (float)cut.prefix / kFix;
+        const float cumulative = __fdiv_rn((float)cut.prefix, kFix);
         const unsigned long long r = toFix(coin * cumulative);
         __syncthreads();
         const Found pick = radixFind(a, inv, cutoff, r, hist, scratch, sInt);

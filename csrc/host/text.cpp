@@ -1,5 +1,7 @@
 #include "text.hpp"
 
+#include "../common/dl_expf.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -277,12 +279,22 @@ int32_t Sampler::sample(float *logits) {
         for (int i = 1; i < n; i++) if (logits[i] > logits[best]) best = i;
         return best;
     }
-    for (int i = 0; i < n; i++) logits[i] /= temperature_;
-    softmaxInPlace(logits, n);
+    // softmax with the shared exp (csrc/common/dl_expf.h) and an integer normaliser: bit-identical to the device sampler
+    float mx = -INFINITY;
+    for (int i = 0; i < n; i++) { logits[i] /= temperature_; mx = std::max(mx, logits[i]); }
+    uint64_t sumFix = 0;
+    for (int i = 0; i < n; i++) { logits[i] = expNeg(logits[i] - mx); sumFix += (uint64_t)(logits[i] * 1099511627776.0f); }
+    const float inv = 1.0f / ((float)sumFix / 1099511627776.0f);
+    for (int i = 0; i < n; i++) logits[i] *= inv;
     const float coin = rng_.nextF32();
+    // Prefix sums run in 2^-40 fixed point (64-bit integers): exact and order independent, so the device sampler
+    // (csrc/cuda/sampler.cu), which adds the same terms in parallel, reaches the same decisions. The reference accumulates the same
+    // sums in float (src/tokenizer.cpp:405-467); the two differ only when the coin falls within float rounding of a boundary.
+    auto fix = [](float p) { return (uint64_t)(p * 1099511627776.0f); };
     if (topp_ <= 0.f || topp_ >= 1.f) {
-        float cdf = 0.f;
-        for (int i = 0; i < n; i++) { cdf += logits[i]; if (coin < cdf) return i; }
+        uint64_t cdf = 0;
+        const uint64_t c = fix(coin);
+        for (int i = 0; i < n; i++) { cdf += fix(logits[i]); if (c < cdf) return i; }
         return n - 1;
     }
     // nucleus: tokens below (1-p)/(n-1) can never be inside the top-p set, drop them before sorting
@@ -292,15 +304,16 @@ int32_t Sampler::sample(float *logits) {
     std::sort(candidates_.begin(), candidates_.end(), [](const std::pair<float, int32_t> &a, const std::pair<float, int32_t> &b) {
         return a.first > b.first || (a.first == b.first && a.second < b.second);
     });
-    float cumulative = 0.f;
+    uint64_t cumulative = 0;
+    const uint64_t target = fix(topp_);
     int last = (int)candidates_.size() - 1;
     for (int i = 0; i < (int)candidates_.size(); i++) {
-        cumulative += candidates_[i].first;
-        if (cumulative > topp_) { last = i; break; }
+        cumulative += fix(candidates_[i].first);
+        if (cumulative > target) { last = i; break; }
     }
-    const float r = coin * cumulative;
-    float cdf = 0.f;
-    for (int i = 0; i <= last; i++) { cdf += candidates_[i].first; if (r < cdf) return candidates_[i].second; }
+    const uint64_t r = fix(coin * ((float)cumulative / 1099511627776.0f));
+    uint64_t cdf = 0;
+    for (int i = 0; i <= last; i++) { cdf += fix(candidates_[i].first); if (r < cdf) return candidates_[i].second; }
     return candidates_[last].second;
 }
 

@@ -41,7 +41,7 @@ def test_device_sampler_matches_host_sampler(temperature, topp):
         agree = sum(a == b for a, b in zip(dev, ref))
         # identical generator stream and ordering rule; the softmax arithmetic differs in the last ulps (parallel sums, ex2 vs libm),
         # so a coin within ~1e-6 of a boundary may land on the neighbouring token
-        assert agree >= 245, (agree, [(a, b) for a, b in zip(dev, ref) if a != b][:5])
+        assert agree >= 249, (agree, [(a, b) for a, b in zip(dev, ref) if a != b][:5])
 
 
 def test_device_sampler_is_reproducible_and_in_range():

@@ -153,6 +153,9 @@ def test_python_and_native_servers_agree(stub):
             self.produced += 1
             return eos if self.produced > 12 else (token * 7 + pos * 13 + 5) % regular
 
+        def next_token(self, token, pos, sampler):
+            return self.forward_greedy(token, pos)
+
     port_py = _free_port()
     args = parse_args(["--model", "stub.m", "--tokenizer", tok_path, "--host", "127.0.0.1", "--port", str(port_py), "--temperature", "0"], False)
     ctx = SimpleNamespace(args=args, sess=None, inference=FakeInference(), tokenizer=tok, sampler=H.Sampler(tok.vocab_size, 0.0, 0.9, 1),
