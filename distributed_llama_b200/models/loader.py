@@ -239,3 +239,67 @@ def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="
     torch.cuda.synchronize(device)
     W.bytes_uploaded = up.bytes
     return W
+
+
+def synthetic_device_weights(cfg, rank: int = 0, n_ranks: int = 1, device="cuda", moe_mode: str = "auto", seed: int = 1234,
+                             max_seq_len: int = 0) -> DeviceWeights:
+    """Random-init weights of architecture `cfg`, created directly in the device layout of this rank (no `.m` file, no upload):
+    used to benchmark the large configurations (Qwen3-14B, Qwen3-30B-A3B, Llama-3.3-70B) whose 11-40 GB files would take minutes
+    to write on a fresh box. Shapes, partitioning (row / column slices, KV-head replication, expert placement) and value
+    statistics follow load_device_weights / write_synthetic_model; the values themselves are not those of a file with that seed."""
+    import io
+    from ..formats.model_file import write_model_header
+    from .config import ARCH_QWEN3, ARCH_QWEN3_MOE
+    H = host()
+    buf = io.BytesIO()
+    write_model_header(buf, cfg.header_params(quants.F_Q40))
+    h = H.parse_model_header(buf.getvalue(), 1 << 50, max_seq_len)
+    if moe_mode == "auto":
+        moe_mode = "ep" if (h.n_experts > 0 and n_ranks > 1 and (h.ff_dim // n_ranks) % 256 != 0 and h.n_experts % n_ranks == 0) else "tp"
+    ep = h.n_experts > 0 and moe_mode == "ep" and n_ranks > 1
+    kv_rep = 1
+    if n_ranks > h.n_kv_heads:
+        if n_ranks % h.n_kv_heads or (h.n_heads // h.n_kv_heads) % (n_ranks // h.n_kv_heads):
+            raise ValueError("nRanks must be a multiple of nKvHeads that divides the query heads of a KV group")
+        kv_rep = n_ranks // h.n_kv_heads
+    hd, dim = h.head_dim, h.dim
+    nh, nkv = h.n_heads // n_ranks, (1 if kv_rep > 1 else h.n_kv_heads // n_ranks)
+    q0, kv0 = nh * hd, nkv * hd
+    ff0 = h.ff_dim if ep else h.ff_dim // n_ranks
+    v0 = h.vocab_size // n_ranks
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + 7919 * rank)
+
+    def q40(d, n, std, lead=1):
+        w = DeviceQ40.empty(d, n, device, lead=lead)
+        w.qs.random_(-2 ** 31, 2 ** 31 - 1, generator=g)
+        w.scales.copy_(((std / 4.61) * (0.7 + 0.6 * torch.rand(w.scales.shape, device=device, generator=g))).half())
+        return w
+
+    def norm(n):
+        return (1.0 + 0.1 * torch.randn(n, device=device, generator=g)).float()
+
+    ge = torch.Generator(device=device)
+    ge.manual_seed(seed)      # the embedding is replicated: same values on every rank
+    emb = torch.randn(h.vocab_size, dim, device=device, generator=ge)
+    W = DeviceWeights(header=h, rank=rank, n_ranks=n_ranks, n_heads=nh, n_kv_heads=nkv, ff_dim=ff0, vocab=v0, embedding=emb,
+                      final_norm=norm(dim), wcls=q40(v0, dim, dim ** -0.5),
+                      rope=torch.from_numpy(np.asarray(H.build_rope_table(h, h.seq_len))).to(device))
+    n_exp = max(h.n_experts, 1)
+    first_exp, n_local = (rank * (h.n_experts // n_ranks), h.n_experts // n_ranks) if ep else (0, n_exp)
+    W.first_expert, W.n_local_experts, W.moe_mode = first_exp, (n_local if h.n_experts > 0 else 0), ("ep" if ep else "tp")
+    gn = torch.Generator(device=device)
+    gn.manual_seed(seed + 1)   # replicated tensors (norms, router gates)
+    for _ in range(h.n_layers):
+        L = LayerWeights(qkv=q40(q0 + 2 * kv0, dim, dim ** -0.5), wo=q40(dim, q0, 0.5 * (h.n_heads * hd) ** -0.5),
+                         w13=q40(2 * ff0, dim, dim ** -0.5, lead=n_local), w2=q40(dim, ff0, 0.5 * h.ff_dim ** -0.5, lead=n_local),
+                         norm0=(1.0 + 0.1 * torch.randn(dim, device=device, generator=gn)), norm1=(1.0 + 0.1 * torch.randn(dim, device=device, generator=gn)))
+        if h.qk_norm:
+            L.q_norm = 1.0 + 0.1 * torch.randn(hd, device=device, generator=gn)
+            L.k_norm = 1.0 + 0.1 * torch.randn(hd, device=device, generator=gn)
+        if h.n_experts > 0:
+            L.moe_gate = torch.randn(h.n_experts, dim, device=device, generator=gn) * dim ** -0.5
+        W.layers.append(L)
+    torch.cuda.synchronize(device)
+    W.bytes_uploaded = 0
+    return W
