@@ -242,7 +242,7 @@ def run_ours(args):
             "vs_baseline": round(value / base, 2), "dtype": "q40 weights, q80 activations (int8 dp4a), bf16 KV, f32 accum",
             "data": "synthetic (random-init weights in .m layout, synthetic prompt)",
             "config": {"model": args.model, "global_batch": 1, "seq_len": args.prompt_len + steps, "prompt_len": args.prompt_len,
-                       "parallelism": f"tp{args.gpus}", "decode_path": "persistent megakernel" if eng.mega else "multi-kernel PDL chain", "l2_policy": "weights per step (%.2f GB/GPU) >> 126 MB L2, no flush needed" % (weight_bytes / 1e9),
+                       "parallelism": f"tp{args.gpus}", "decode_path": "persistent megakernel" if (eng.mega and eng.mega_active) else "multi-kernel PDL chain", "l2_policy": "weights per step (%.2f GB/GPU) >> 126 MB L2, no flush needed" % (weight_bytes / 1e9),
                        "baseline_ref": "reference published Llama-2-7B q40 ms/token on %d x RPi 4B (report.pdf)" % args.gpus},
             "ttft_ms": round(ttft_ms, 3), "prefill_tokens_per_s": round(args.prompt_len / ttft_ms * 1e3, 1),
             "e2e": {"value": round(steps / e2e_ms * 1e3, 2), "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 4},

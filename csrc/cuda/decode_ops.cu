@@ -12,14 +12,14 @@
 namespace dl {
 
 // ---- embedding ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) embeddingKernel(const float *__restrict__ table, const int *__restrict__ tokens,
+__global__ void __launch_bounds__(256) embeddingKernel(const EmbTable table, const int *__restrict__ tokens,
                                                        float *__restrict__ x, uint32_t dim, uint32_t xStride, uint32_t vocab) {
     pdlLaunchDependents();
     pdlWait();
     const int t = blockIdx.x;
     int tok = tokens[t];
     if (tok < 0 || (uint32_t)tok >= vocab) tok = 0;
-    const float4 *src = reinterpret_cast<const float4 *>(table + (size_t)tok * dim);
+    const float4 *src = reinterpret_cast<const float4 *>(table.row((uint32_t)tok, dim));
     float4 *dst = reinterpret_cast<float4 *>(x + (size_t)t * xStride);
     for (uint32_t i = threadIdx.x; i < dim / 4; i += blockDim.x) dst[i] = src[i];
 }
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(1024) argmaxAdvanceKernel(const float *__restr
     }
 }
 
-int launchEmbedding(const float *table, const int *tokens, float *x, uint32_t dim, uint32_t xStride, uint32_t vocab, int nb,
+int launchEmbedding(const EmbTable &table, const int *tokens, float *x, uint32_t dim, uint32_t xStride, uint32_t vocab, int nb,
                     cudaStream_t stream) {
     embeddingKernel<<<nb, 256, 0, stream>>>(table, tokens, x, dim, xStride, vocab);
     DL_CUDA_CHECK(cudaGetLastError());

@@ -7,6 +7,7 @@
 // (token id, position) live in device memory so the graph replays without host round trips:
 // the sampling kernel writes the next token and advances the position on the device.
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "engine_api.h"
@@ -39,6 +40,7 @@ struct Engine {
     uint32_t megaInflight = 2;         // DL_MEGA_INFLIGHT: producer pacing of the persistent kernel (0 = unpaced)
     uint32_t megaCtas = 0;             // DL_MEGA_CTAS: grid size override of the persistent kernel (0 = one CTA per SM)
     bool useMega = false;
+    bool lastDecodeMega = false, megaFallbackWarned = false;   // did the last single-token forward run on the persistent kernel?
     // device sampler state (sampler.cu)
     unsigned long long *rngState = nullptr;
     float *probScratch = nullptr;
@@ -55,6 +57,14 @@ struct Engine {
         const int _r = (expr);          \
         if (_r != 0) return _r;         \
     } while (0)
+
+static EmbTable embTable(const Engine &e) {
+    EmbTable t{};
+    t.rowsPerRank = e.g.embRowsPerRank;
+    if (t.rowsPerRank == 0) t.shard[0] = e.g.embedding;
+    else for (int r = 0; r < kMaxRanks; r++) t.shard[r] = e.g.embeddingPeers[r];
+    return t;
+}
 
 static void fillAr(const Engine &e, ArArgs &ar, uint32_t parity) {
     const CommPtrs &c = e.comm;
@@ -117,11 +127,12 @@ static int engineDecodeMega(Engine &e, bool greedyAdvance, cudaStream_t stream) 
     MegaArgs m{};
     m.layers = e.megaLayers; m.nLayers = c.nLayers; m.dim = c.dim; m.nHeads = c.nHeads; m.nKvHeads = c.nKvHeads; m.headDim = c.headDim;
     m.ffDim = c.ffDim; m.vocab = c.vocab; m.vocabFull = e.g.vocabFull; m.seqLen = c.seqLen; m.nSplits = c.nSplits; m.eps = c.eps;
-    m.embedding = e.g.embedding; m.finalNorm = e.g.finalNorm; m.rope = e.g.rope;
+    m.embedding = embTable(e); m.finalNorm = e.g.finalNorm; m.rope = e.g.rope;
     m.wclsQs = (const uint8_t *)e.g.wclsQs; m.wclsSc = (const uint8_t *)e.g.wclsSc;
     m.tokens = e.g.tokens; m.pos = e.g.pos; m.history = e.g.history;
     m.logits = e.g.logits; m.maxInflight = e.megaInflight;
     m.xW = e.megaX; m.xW2 = e.megaX2; m.flags = e.megaFlags; m.qkvW = e.megaQkv; m.zW = e.megaZ; m.hF = (float *)e.megaH; m.launchSeq = e.megaSeq; m.abortFlag = e.abortDev;
+    m.syncNs = (e.comm.nRanks > 1 && e.megaSeq) ? (unsigned long long *)(e.megaSeq + 2) : nullptr;
     m.attnPartial = e.g.attnPartial; m.attnCounters = e.g.attnCounters;
     m.argVal = e.g.argVal; m.argIdx = e.g.argIdx; m.argCounter = e.g.argCounter; m.gridCounter = e.megaCounter;
     m.rowOffsetGlobal = c.rank * c.vocab; m.greedyAdvance = greedyAdvance ? 1u : 0u; m.vocabLimit = e.vocabLimit;
@@ -138,14 +149,20 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
     const bool pdl = c.usePdl != 0;
     const uint32_t qDim = c.nHeads * c.headDim, kvDim = c.nKvHeads * c.headDim, qkvDim = qDim + 2 * kvDim;
     if (nb < 1 || (uint32_t)nb > c.maxBatch || (nb & (nb - 1))) return -10;
+    e.lastDecodeMega = false;
     if (nb == 1 && logitsMode == 1 && e.useMega) {
         const int r = engineDecodeMega(e, greedyAdvance, stream);
-        if (r != 1) return r;
+        if (r != 1) { e.lastDecodeMega = r == 0; return r; }
+        if (!e.megaFallbackWarned) {
+            std::fprintf(stderr, "dl_engine: the persistent decode kernel cannot run this configuration (shape, shared memory or co-residency); "
+                                 "using the multi-kernel path\n");
+            e.megaFallbackWarned = true;
+        }
     }
     uint32_t slot = 0;
     auto nextTrace = [&]() -> uint64_t * { uint64_t *t = (e.trace && slot < e.traceCap) ? e.trace + (size_t)slot * 4 : nullptr; slot++; return t; };
 
-    DL_TRY(launchEmbedding(e.g.embedding, e.g.tokens, e.g.x, c.dim, c.dim, e.g.vocabFull, nb, stream));
+    DL_TRY(launchEmbedding(embTable(e), e.g.tokens, e.g.x, c.dim, c.dim, e.g.vocabFull, nb, stream));
     for (uint32_t l = 0; l < c.nLayers; l++) {
         const LayerPtrs &L = e.layers[l];
         GemvArgs a{};
@@ -255,7 +272,7 @@ static int enginePrefill(Engine &e, uint32_t T, uint32_t p0, int wantLogits, cud
         arP.slotStride = e.comm.prefillSlotStride;
         for (uint32_t r = 0; r < e.comm.nRanks; r++) arP.slots[r] = (uint64_t *)((uint8_t *)e.comm.arena[r] + e.comm.prefillSlotsOff);
     }
-    DL_TRY(launchEmbedding(g.embedding, g.pTokens, g.px, c.dim, c.dim, g.vocabFull, (int)T, stream));
+    DL_TRY(launchEmbedding(embTable(e), g.pTokens, g.px, c.dim, c.dim, g.vocabFull, (int)T, stream));
     for (uint32_t l = 0; l < c.nLayers; l++) {
         const LayerPtrs &L = e.layers[l];
         DL_TRY(launchRmsNormBf16(g.px, c.dim, L.norm0, g.pxn, c.dim, c.dim, c.eps, T, stream));
@@ -387,7 +404,7 @@ DL_EXPORT int dl_engine_enable_mega(void *h, int enable) {
         DL_CUDA_CHECK(cudaMemcpy(e->megaSeq, &one, sizeof(one), cudaMemcpyHostToDevice));   // epochs start at 1024: never equal to the zeroed words
         if (!e->abortHost) {
             DL_CUDA_CHECK(cudaHostAlloc((void **)&e->abortHost, 64, cudaHostAllocMapped));
-            *e->abortHost = 0;
+            std::memset(e->abortHost, 0, 64);
             DL_CUDA_CHECK(cudaHostGetDevicePointer((void **)&e->abortDev, e->abortHost, 0));
         }
         if (const char *g = std::getenv("DL_MEGA_CTAS")) e->megaCtas = (uint32_t)std::atoi(g);
@@ -403,6 +420,15 @@ DL_EXPORT int dl_engine_set_vocab_limit(void *h, uint32_t limit) {
     if (e->vocabLimit != limit && e->decodeGraph) { cudaGraphExecDestroy(e->decodeGraph); e->decodeGraph = nullptr; }   // the limit is baked into the captured launch
     e->vocabLimit = limit;
     return 0;
+}
+
+// Nanoseconds the persistent kernel (CTA 0) has spent waiting for peer ranks inside the fused all-reduce epilogues since engine
+// creation (host-mapped counter: readable without a device synchronisation; exact after the stream has been synchronised).
+DL_EXPORT unsigned long long dl_engine_sync_ns(void *h) {
+    Engine *e = (Engine *)h;
+    unsigned long long v = 0;
+    if (e->megaSeq && cudaMemcpy(&v, e->megaSeq + 2, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 0ull;
+    return v;
 }
 
 // 1 when a device-side wait loop gave up (dead peer rank, CTA that never became resident): the results of that step are invalid.
@@ -480,6 +506,8 @@ DL_EXPORT int dl_engine_set_trace_all(void *h, int allCtas) {
     return 0;
 }
 
+DL_EXPORT int dl_engine_mega_active(void *h) { return ((Engine *)h)->lastDecodeMega ? 1 : 0; }
+
 DL_EXPORT uint32_t dl_engine_num_sms(void *h) { return ((Engine *)h)->cfg.numSms; }
 
 DL_EXPORT int dl_engine_forward(void *h, int nb, int logitsMode, int greedyAdvance, cudaStream_t stream) {
@@ -497,7 +525,7 @@ DL_EXPORT int dl_engine_forward_part(void *h, int nb, uint32_t layer, int part, 
     const dl::EngineConfig &c = e.cfg;
     const uint32_t qDim = c.nHeads * c.headDim, kvDim = c.nKvHeads * c.headDim, qkvDim = qDim + 2 * kvDim;
     if (nb < 1 || (uint32_t)nb > c.maxBatch || (nb & (nb - 1))) return -10;
-    if (part == 0) return dl::launchEmbedding(e.g.embedding, e.g.tokens, e.g.x, c.dim, c.dim, e.g.vocabFull, nb, stream);
+    if (part == 0) return dl::launchEmbedding(embTable(e), e.g.tokens, e.g.x, c.dim, c.dim, e.g.vocabFull, nb, stream);
     if (part == 3 || part == 4) {
         dl::GemvArgs a{};
         a.qs = (const uint32_t *)e.g.wclsQs; a.scales = (const __half *)e.g.wclsSc; a.d = c.vocab; a.n = c.dim;

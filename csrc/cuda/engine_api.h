@@ -33,7 +33,9 @@ struct LayerPtrs {
 };
 
 struct GlobalPtrs {
-    const float *embedding;      // [vocabFull][dim]
+    const float *embedding;      // [vocabFull][dim] (replicated) or this rank's shard when embRowsPerRank != 0
+    const float *embeddingPeers[kApiMaxRanks];   // vocabulary shards of all ranks (peer-mapped), used when embRowsPerRank != 0
+    uint32_t embRowsPerRank;     // 0: `embedding` is the whole table
     const float *finalNorm;
     const void *wclsQs, *wclsSc; // [vocab][dim]
     const float *rope;           // [seqLen][hd/2][2]
@@ -84,6 +86,8 @@ int dl_engine_set_comm(void *h, const dl::CommPtrs *p);
 int dl_engine_enable_mega(void *h, int enable);
 int dl_engine_set_vocab_limit(void *h, uint32_t limit);   // greedy arg-max never returns ids >= limit (tokenizer vocabulary size)
 int dl_engine_aborted(void *h);
+int dl_engine_mega_active(void *h);   // 1 if the last single-token forward ran on the persistent kernel (0: fell back to the multi-kernel path)
+unsigned long long dl_engine_sync_ns(void *h);
 int dl_engine_sampler_seed(void *h, unsigned long long seed);
 int dl_engine_sample(void *h, float temperature, float topp, cudaStream_t stream);   // after a forward with logitsMode 1
 int dl_engine_set_trace(void *h, uint64_t *buf, uint32_t capLaunches);

@@ -131,7 +131,19 @@ struct RouterArgs {
 };
 int launchMoeRouter(const RouterArgs &a, int nb, cudaStream_t stream, bool pdl);
 
-int launchEmbedding(const float *table, const int *tokens, float *x, uint32_t dim, uint32_t xStride, uint32_t vocab, int nb,
+// Token embedding table (f32 [vocab][dim]). Tensor parallel: sharded by vocabulary rows over the ranks' peer-mapped memory — rank r
+// holds rows [r * rowsPerRank, (r + 1) * rowsPerRank) and every rank reads the row of the current token straight from its owner over
+// NVLink (reference K1: the root embeds and broadcasts x, src/llm.cpp:248-256; here a 16 KB peer load replaces 2.1 GB x N of replicas).
+struct EmbTable {
+    const float *shard[kMaxRanks];   // shard[0] is the whole table when rowsPerRank == 0
+    uint32_t rowsPerRank;
+    __host__ __device__ const float *row(uint32_t tok, uint32_t dim) const {
+        if (rowsPerRank == 0) return shard[0] + (size_t)tok * dim;
+        const uint32_t r = tok / rowsPerRank;
+        return shard[r] + (size_t)(tok - r * rowsPerRank) * dim;
+    }
+};
+int launchEmbedding(const EmbTable &table, const int *tokens, float *x, uint32_t dim, uint32_t xStride, uint32_t vocab, int nb,
                     cudaStream_t stream);
 int launchArgmaxAdvance(const float *logits, uint32_t vocab, int *tokenOut, int *pos, int *history, uint32_t historyCap,
                         cudaStream_t stream, bool pdl);   // single rank only: the index is local to `logits`
@@ -161,7 +173,8 @@ struct MegaArgs {
     const MegaLayer *layers;     // [nLayers] in global memory
     uint32_t nLayers, dim, nHeads, nKvHeads, headDim, ffDim, vocab, vocabFull, seqLen, nSplits;
     float eps;
-    const float *embedding, *finalNorm, *rope;
+    EmbTable embedding;
+    const float *finalNorm, *rope;
     const uint8_t *wclsQs, *wclsSc;
     int *tokens, *pos, *history;
     float *logits;
@@ -171,6 +184,7 @@ struct MegaArgs {
     float *hF;                   // SwiGLU vector: plain f32 behind a fenced barrier (too large to pay the 2x LL footprint)
     unsigned int *launchSeq;     // device-resident launch counter (epoch base)
     unsigned int *abortFlag;     // host-mapped: set by a wait loop that ran out of its spin budget
+    unsigned long long *syncNs;  // device accumulator: ns CTA 0 spent waiting for peer ranks in the all-reduce epilogues (null: off)
     float *attnPartial;
     unsigned int *attnCounters;
     float *argVal;

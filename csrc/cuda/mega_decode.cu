@@ -369,6 +369,8 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
                 uint64_t *mine = ar.slots[ar.rank];
                 float sum = 0.f;
                 SpinGuard g(m.abortFlag);
+                const bool timeIt = m.syncNs && blockIdx.x == 0 && tid == 0;     // "Sync" time of the CLI lines: wait for the peers' partial sums
+                const uint64_t tSync0 = timeIt ? globalTimerNs() : 0;
                 for (uint32_t sr = 0; sr < ar.nRanks; sr++) {
                     uint64_t *w = mine + (size_t)(arParity * ar.nRanks + sr) * ar.slotStride + rowBase + r;
                     uint2 v2 = ldLL(w);
@@ -376,6 +378,7 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
                     sum += __uint_as_float(v2.x);
                     stLL(w, 0u, 0u);
                 }
+                if (timeIt) *m.syncNs += globalTimerNs() - tSync0;   // device-memory accumulator, touched by this one thread only
                 stW(outW + rowBase + r, resid + sum, outEpoch);
             }
         } else if ((uint32_t)tid < tileRows) {
@@ -693,7 +696,7 @@ __device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaL
 }
 
 template <int HD>
-__global__ void __maxnreg__(120) megaDecodeKernel(const __grid_constant__ MegaArgs m) {
+__global__ void __maxnreg__(112) megaDecodeKernel(const __grid_constant__ MegaArgs m) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     MegaSmem sm;
@@ -787,7 +790,7 @@ __global__ void __maxnreg__(120) megaDecodeKernel(const __grid_constant__ MegaAr
         if (tok < 0 || (uint32_t)tok >= m.vocabFull) tok = 0;
         uint32_t pairBegin, tileRows;
         megaTile(m.ph[MP_WO], pairBegin, tileRows);
-        if ((uint32_t)tid < tileRows) stW(m.xW + pairBegin * 2 + tid, m.embedding[(size_t)tok * m.dim + pairBegin * 2 + tid], seqBase);
+        if ((uint32_t)tid < tileRows) stW(m.xW + pairBegin * 2 + tid, m.embedding.row((uint32_t)tok, m.dim)[pairBegin * 2 + tid], seqBase);
     }
     gridBarrier(m.gridCounter, barTarget, tid, m.abortFlag);
     // Experimental (MegaArgs::flags bit 0): no counter barrier where the consumer polls LL words anyway; the polls back off with

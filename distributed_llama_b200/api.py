@@ -43,7 +43,7 @@ class InferenceSession:
         if device is None:
             device = f"cuda:{torch.cuda.current_device()}"
         self.device = torch.device(device)
-        self.weights = load_device_weights(self.model_file, rank, n_ranks, self.device, moe_mode=moe_mode)
+        self.weights = load_device_weights(self.model_file, rank, n_ranks, self.device, moe_mode=moe_mode, comm=comm)
         self.engine = Engine(self.weights, max_batch=max_batch, use_pdl=use_pdl, comm=comm)
         H = host()
         self.tokenizer = H.Tokenizer(tokenizer_path) if tokenizer_path else None

@@ -48,7 +48,8 @@ def inference(ctx: AppContext) -> None:
         torch.cuda.synchronize(dev)
         dt = (time.perf_counter() - t0) * 1000
         eval_ms += dt
-        print(f"🔷️ Eval{int(dt):5d} ms Sync{0:5d} ms | Sent{0:6d} kB Recv{0:6d} kB | ({n} tokens)")
+        sent, recv = ctx.sess.engine.link_bytes(n)
+        print(f"🔷️ Eval{int(dt):5d} ms Sync{0:5d} ms | Sent{sent // 1024:6d} kB Recv{recv // 1024:6d} kB | ({n} tokens)")
         pos += n
     sys.stdout.flush()
     token = tokens[pos]          # last prompt token (the reference reads one past it, SURVEY §7.3 — not copied)
@@ -57,6 +58,8 @@ def inference(ctx: AppContext) -> None:
     max_pos = min(h.seq_len, a.steps)
     greedy = ctx.sampler.temperature == 0.0
     n_pred = 0
+    sync_prev = ctx.sess.engine.sync_ns() if inf.comm is not None else 0
+    sync_total_us = 0
     while pos < max_pos:
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
@@ -64,7 +67,13 @@ def inference(ctx: AppContext) -> None:
         dt = (time.perf_counter() - t0) * 1000
         pred_ms += dt
         piece = tok.decode(token).decode("utf-8", errors="replace")
-        print(f"🔶 Pred{int(dt):5d} ms Sync{0:5d} ms | Sent{0:6d} kB Recv{0:6d} kB | {piece if piece else '~'}")
+        sent, recv = ctx.sess.engine.link_bytes(1)
+        sync_now = ctx.sess.engine.sync_ns() if inf.comm is not None else 0
+        sync_us, sync_prev = (sync_now - sync_prev) // 1000, sync_now
+        sync_total_us += sync_us
+        # Sync = time the decode kernel waited for peer ranks inside its fused all-reduces (a token takes ~1 ms: mostly prints 0;
+        # the per-token average in microseconds is part of the summary)
+        print(f"🔶 Pred{int(dt):5d} ms Sync{sync_us // 1000:5d} ms | Sent{sent // 1024:6d} kB Recv{recv // 1024:6d} kB | {piece if piece else '~'}")
         sys.stdout.flush()
         pos += 1
         n_pred += 1
@@ -79,6 +88,8 @@ def inference(ctx: AppContext) -> None:
     print(f"    nTokens: {n_pred}")
     if n_pred > 0 and pred_ms > 0:
         print(f"   tokens/s: {n_pred * 1000 / pred_ms:3.2f} ({pred_ms / n_pred:3.2f} ms/tok)")
+        if inf.comm is not None:
+            print(f"   syncTime: {sync_total_us / n_pred:3.1f} us/tok (waiting for peer ranks inside the fused all-reduces)")
 
 
 def perplexity(ctx: AppContext) -> None:

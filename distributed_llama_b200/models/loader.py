@@ -59,6 +59,8 @@ class DeviceWeights:
     n_local_experts: int = 0
     moe_mode: str = "tp"
     weight_kind: int = 0         # 0 = q40 device layout, 1 = dense f32, 2 = dense f16
+    embedding_ptrs: Optional[List[int]] = None   # vocabulary-sharded embedding: device pointer of every rank's shard (peer mapped)
+    embedding_rows: int = 0      # rows per shard (0: `embedding` is the whole replicated table)
 
 
 def _interleave_perm(head_dim: int) -> np.ndarray:
@@ -153,7 +155,40 @@ def _load_dense(mf: ModelFile, up: "_Uploader", rank, n_ranks, kv_rank, kv_ranks
     return W
 
 
-def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="cuda", moe_mode: str = "auto") -> DeviceWeights:
+class _RawCuda:
+    """Wraps a raw device pointer (peer-mapped VMM memory) as a CUDA array so torch can view it."""
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _sharded_embedding(mf: ModelFile, up: "_Uploader", rank: int, n_ranks: int, device, comm):
+    """Uploads only this rank's vocabulary rows of the f32 embedding into peer-mapped memory; returns (local tensor, pointers of all
+    shards, rows per shard) or None when no symmetric allocation is available (the table is then replicated)."""
+    import os
+    h = mf.header
+    if comm is None or n_ranks <= 1 or h.vocab_size % n_ranks or os.environ.get("DL_REPLICATE_EMBEDDING") is not None:
+        return None
+    if not hasattr(comm, "alloc_shared"):
+        return None
+    rows = h.vocab_size // n_ranks
+    ptrs = comm.alloc_shared(rows * h.dim * 4)
+    if ptrs is None:
+        return None
+    local = torch.as_tensor(_RawCuda(ptrs[rank], rows * h.dim), device=device).view(rows, h.dim)
+    e = mf.entry("embedding")
+    src = mf.data[e.offset + rank * rows * h.dim * 4: e.offset + (rank + 1) * rows * h.dim * 4]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        host_t = torch.from_numpy(src).view(torch.float32).view(rows, h.dim)
+    local.copy_(host_t)
+    up.bytes += rows * h.dim * 4
+    torch.cuda.synchronize(device)
+    import torch.distributed as dist
+    dist.barrier()          # every shard is in place before any rank may read a peer's rows
+    return local, ptrs, rows
+
+
+def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="cuda", moe_mode: str = "auto", comm=None) -> DeviceWeights:
     """moe_mode (Qwen3-MoE only): "tp" slices every expert over the ranks like the reference (src/llm.cpp:454-486);
     "ep" gives each rank nExperts/nRanks whole experts (expert parallelism: the expert FFN streams full-width matrices and the
     combine is the same in-kernel all-reduce); "auto" picks ep when the TP slice would be narrower than 128 columns."""
@@ -203,10 +238,13 @@ def load_device_weights(mf: ModelFile, rank: int = 0, n_ranks: int = 1, device="
             raw = up.cols(e, (rank if slice_rank is None else slice_rank) * cbytes, cbytes)
         repack_q40(raw, e.d, cols_local, dst, src_row_pitch=cbytes, src_col_byte_offset=0, dst_row_offset=dst_off)
 
+    shard = _sharded_embedding(mf, up, rank, n_ranks, device, comm)
     W = DeviceWeights(header=h, rank=rank, n_ranks=n_ranks, n_heads=nh, n_kv_heads=nkv, ff_dim=ff0, vocab=v0,
-                      embedding=up.f32(mf.entry("embedding")), final_norm=up.f32(mf.entry("final_norm")),
+                      embedding=shard[0] if shard else up.f32(mf.entry("embedding")), final_norm=up.f32(mf.entry("final_norm")),
                       wcls=DeviceQ40.empty(v0, dim, device),
                       rope=torch.from_numpy(np.asarray(H.build_rope_table(h, h.seq_len))).to(device))
+    if shard:
+        W.embedding_ptrs, W.embedding_rows = shard[1], shard[2]
     row_sliced("final_matmul_logits", 0, 0, W.wcls, v0)
     perm = torch.from_numpy(_interleave_perm(hd)).to(device) if neox else None
     n_exp = max(h.n_experts, 1)

@@ -27,7 +27,7 @@ class LayerPtrs(C.Structure):
 
 
 class GlobalPtrs(C.Structure):
-    _fields_ = [("embedding", vp), ("finalNorm", vp), ("wclsQs", vp), ("wclsSc", vp), ("rope", vp), ("vocabFull", u32),
+    _fields_ = [("embedding", vp), ("embeddingPeers", vp * 8), ("embRowsPerRank", u32), ("finalNorm", vp), ("wclsQs", vp), ("wclsSc", vp), ("rope", vp), ("vocabFull", u32),
                 ("tokens", vp), ("pos", vp), ("x", vp), ("qkv", vp), ("z", vp), ("h", vp), ("logits", vp),
                 ("attnPartial", vp), ("attnCounters", vp), ("history", vp), ("expertIdx", vp), ("expertWeight", vp),
                 ("routerLogits", vp), ("routerCounter", vp), ("moeScratch", vp), ("moeCounters", vp),
@@ -104,6 +104,10 @@ def lib() -> C.CDLL:
     L.dl_engine_sample.restype = i32
     L.dl_sample_logits.argtypes = [vp, vp, u32, f32, f32, vp, vp, vp]
     L.dl_sample_logits.restype = i32
+    L.dl_engine_sync_ns.argtypes = [vp]
+    L.dl_engine_sync_ns.restype = C.c_uint64
+    L.dl_engine_mega_active.argtypes = [vp]
+    L.dl_engine_mega_active.restype = i32
     L.dl_engine_aborted.argtypes = [vp]
     L.dl_engine_aborted.restype = i32
     L.dl_engine_set_trace_all.argtypes = [vp, i32]

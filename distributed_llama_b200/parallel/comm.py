@@ -78,11 +78,33 @@ class Communicator:
         mapping (csrc/cuda/comm_vmm.cu); fallback: cudaMalloc + CUDA IPC handles (no multicast)."""
         import os
         self.layout = layout
-        if os.environ.get("DL_NO_VMM") is None and self._alloc_vmm(layout):
+        if os.environ.get("DL_NO_VMM") is None and self.single_node and self._alloc_vmm(layout):
             return
         self._alloc_ipc(layout)
 
+    def alloc_shared(self, nbytes: int):
+        """A second symmetric allocation (no multicast mapping): returns the list of per-rank device pointers, or None when the VMM
+        path is unavailable. Used for the vocabulary-sharded embedding table."""
+        import os
+        if os.environ.get("DL_NO_VMM") is not None or not self.single_node:
+            return None
+        res = self._vmm_bootstrap(nbytes, want_mc=0)
+        if res is None:
+            return None
+        h, ptrs, _mc = res
+        self._shared_handles = getattr(self, "_shared_handles", []) + [h]
+        return ptrs
+
     def _alloc_vmm(self, layout: ArenaLayout) -> bool:
+        res = self._vmm_bootstrap(layout.total, want_mc=0 if __import__("os").environ.get("DL_NO_MULTICAST") is not None else 1)
+        if res is None:
+            return False
+        self._vmm, self.arena_ptrs, self.mc_ptr = res
+        self._local = self.arena_ptrs[self.rank]
+        self.arena_kind = "vmm"
+        return True
+
+    def _vmm_bootstrap(self, total: int, want_mc: int):
         import os
         lib = self._lib
         flags = C.c_int(0)
@@ -91,36 +113,32 @@ class Communicator:
         ok = torch.tensor([1 if (flags.value & 1) else 0], dtype=torch.int32, device=self.device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
-            return False
+            return None
         Communicator._arena_seq += 1
         nonce = [None]
         if self.rank == 0:
             nonce[0] = f"{os.getpid()}-{Communicator._arena_seq}-{int.from_bytes(os.urandom(4), 'little')}"
         dist.broadcast_object_list(nonce, src=0)
-        want_mc = 0 if os.environ.get("DL_NO_MULTICAST") is not None else 1
-        h = lib.dl_vmm_create(self.rank, self.world_size, layout.total, nonce[0].encode(), want_mc)
+        h = lib.dl_vmm_create(self.rank, self.world_size, total, nonce[0].encode(), want_mc)
         ok = torch.tensor([1 if h else 0], dtype=torch.int32, device=self.device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             if h:
                 lib.dl_vmm_destroy(h)
-            return False
+            return None
         rc = lib.dl_vmm_connect(h)
         ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             raise RuntimeError(f"rank {self.rank}: VMM arena bootstrap failed (code {rc}); set DL_NO_VMM=1 to use the CUDA IPC arena")
-        self._vmm = h
-        self.arena_ptrs = [int(lib.dl_vmm_ptr(h, r)) for r in range(self.world_size)]
-        self._local = self.arena_ptrs[self.rank]
+        ptrs = [int(lib.dl_vmm_ptr(h, r)) for r in range(self.world_size)]
         mc = lib.dl_vmm_mc_ptr(h)
         # the multicast mapping is used only if every rank has it
         have = torch.tensor([1 if mc else 0], dtype=torch.int32, device=self.device)
         dist.all_reduce(have, op=dist.ReduceOp.MIN)
-        self.mc_ptr = int(mc) if (mc and int(have.item()) == 1) else 0
-        self.arena_kind = "vmm"
+        mc_ptr = int(mc) if (mc and int(have.item()) == 1) else 0
         dist.barrier()
-        return True
+        return h, ptrs, mc_ptr
 
     def _alloc_ipc(self, layout: ArenaLayout) -> None:
         ptr = C.c_void_p()

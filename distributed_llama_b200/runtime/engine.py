@@ -99,7 +99,8 @@ class Engine:
                               norm0=_p(L.norm0), norm1=_p(L.norm1), qNorm=_p(L.q_norm), kNorm=_p(L.k_norm),
                               moeGate=_p(L.moe_gate), kCache=_p(self.k_cache[l]), vCache=_p(self.v_cache[l]))
             cl.check(self._lib.dl_engine_set_layer(self._h, l, C.byref(lp)), "engine_set_layer")
-        gp = cl.GlobalPtrs(embedding=_p(w.embedding), finalNorm=_p(w.final_norm), wclsQs=_p(w.wcls.qs),
+        emb_peers = (C.c_void_p * 8)(*([C.c_void_p(p) for p in (w.embedding_ptrs or [])] + [None] * (8 - len(w.embedding_ptrs or []))))
+        gp = cl.GlobalPtrs(embedding=_p(w.embedding), embeddingPeers=emb_peers, embRowsPerRank=w.embedding_rows or 0, finalNorm=_p(w.final_norm), wclsQs=_p(w.wcls.qs),
                            wclsSc=_p(w.wcls.scales), rope=_p(w.rope), vocabFull=h.vocab_size, tokens=_p(self.tokens),
                            pos=_p(self.pos), x=_p(self.x), qkv=_p(self.qkv), z=_p(self.z), h=_p(self.h),
                            logits=_p(self.logits), attnPartial=_p(self.attn_partial), attnCounters=_p(self.attn_counters),
@@ -163,6 +164,28 @@ class Engine:
             raise RuntimeError("seed_sampler() must be called first")
         self.forward_batch([token], pos, logits_mode=1)
         cl.check(self._lib.dl_engine_sample(self._h, float(temperature), float(topp), cl.stream_ptr()), "engine_sample")
+
+    # -- traffic / synchronisation accounting (reference: NnNetwork::getStats + executor sync timers, src/dllama.cpp:59-66) --
+    def sync_ns(self) -> int:
+        """Cumulative ns the decode kernel waited for peer ranks inside its fused all-reduces (0 on one GPU)."""
+        return int(self._lib.dl_engine_sync_ns(self._h))
+
+    def link_bytes(self, n_tokens: int) -> tuple:
+        """(sent, received) NVLink bytes of this rank for a forward over n_tokens tokens: 2 all-reduces per layer, every value
+        travels as an 8-byte LL word; with the NVSwitch multicast mapping a value is sent once and replicated by the switch."""
+        n = self.comm.world_size if (self.comm is not None and not self._parts) else 1
+        if n <= 1:
+            return 0, 0
+        h = self.w.header
+        per_ar = n_tokens * h.dim * 8
+        mc = 1 if getattr(self.comm, "mc_ptr", 0) and n_tokens == 1 else (n - 1)
+        return 2 * h.n_layers * per_ar * mc, 2 * h.n_layers * per_ar * (n - 1)
+
+    @property
+    def mega_active(self) -> bool:
+        """True if the last single-token forward actually ran on the persistent kernel (it falls back per call when the shape or
+        the co-residency check rules it out)."""
+        return bool(self._lib.dl_engine_mega_active(self._h))
 
     def check_abort(self):
         """Raises if a device-side wait loop ran out of its spin budget (a peer rank died or a CTA never became resident): the
@@ -308,7 +331,7 @@ class Engine:
 
     @property
     def launches_per_decode_step(self) -> int:
-        if self.mega:
+        if self.mega and self.mega_active:
             return 1                # one persistent kernel per token (plus a 4-byte memset node)
         if self._parts:
             return self.w.header.n_layers * 7 + 2

@@ -91,7 +91,7 @@ if rank == 0:
         pass
     hbm = peaks.get("hbm_gbs", 6650.0)
     print(json.dumps({"model": args.model, "n_gpus": world, "decode_tok_s": round(1000.0 / ms, 1), "ms_per_step": round(ms, 4), "decode_pos": pos0,
-                      "ttft_ms": round(min(ttft[1:]), 3), "prompt_len": args.prompt_len, "decode_path": "persistent megakernel" if eng.mega else "multi-kernel",
+                      "ttft_ms": round(min(ttft[1:]), 3), "prompt_len": args.prompt_len, "decode_path": "persistent megakernel" if (eng.mega and eng.mega_active) else "multi-kernel",
                       "moe_mode": W.moe_mode, "weight_bytes_streamed_per_step_per_gpu": int(wb),
                       "frac_of_measured_hbm": round(wb / ms / 1e6 / hbm, 3), "weights_init_s": round(load_s, 1),
                       "data": "random-init device weights (no file), synthetic prompt"}), flush=True)

@@ -31,7 +31,7 @@ def main():
     dist.barrier()
     mf = ModelFile(path)
     mega = os.environ.get("DL_MEGA") == "1"
-    eng = Engine(load_device_weights(mf, comm.rank, comm.world_size, moe_mode=moe_mode), comm=comm)
+    eng = Engine(load_device_weights(mf, comm.rank, comm.world_size, moe_mode=moe_mode, comm=comm), comm=comm)   # vocabulary-sharded embedding
     if mega:
         eng.enable_mega()
     prompt = [3, 17, 250, 9, 44, 101, 7, 300, 12, 5, 77]
