@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             if (grouped && Teff == 0) continue;
             const uint32_t tc = tcount++;
             const uint32_t acc = tc & 1, accPh = (tc >> 1) & 1;
-            gmBarWaitIdle(&tmemFull[acc], accPh);
+            if (a.debugFlags & 8u) gmBarWait(&tmemFull[acc], accPh); else gmBarWaitIdle(&tmemFull[acc], accPh);
             tcFenceAfter();
             // grouped mode: f is the feature index inside the group's matrix, output rows start at the group's first sorted row
             const uint32_t f = (grouped ? (tile % a.grpTiles) * kGmBlockM : tile * kGmBlockM) + q * 32 + lane;
@@ -627,8 +627,11 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                     }
                 }
                 // the raw chunk now lives in registers: hand the stage back to the TMA producer before the (long) conversion
-                __syncwarp();
-                if (lane == 0) gmBarArrive(&rawEmpty[rs]);
+                const bool lateRelease = (a.debugFlags & 4u) != 0;
+                if (!lateRelease) {
+                    __syncwarp();
+                    if (lane == 0) gmBarArrive(&rawEmpty[rs]);
+                }
                 const uint32_t itA = itR * 4 + grp;
                 const uint32_t s = itA % a.stages, ph = (itA / a.stages) & 1;
                 gmBarWait(&emptyBar[s], ph ^ 1);
@@ -659,7 +662,10 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 }
                 if (!(a.debugFlags & 1u)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) gmBarArrive(&fullBar[s]);
+                if (lane == 0) {
+                    gmBarArrive(&fullBar[s]);
+                    if (lateRelease) gmBarArrive(&rawEmpty[rs]);
+                }
             }
         }
     }
@@ -729,7 +735,7 @@ static size_t tmaGeometry(GemmArgs &a) {
     const size_t bTile = (size_t)a.nTile * 128;
     const size_t budget = 227 * 1024 - 1024 - 512;
     const uint32_t tryA[4] = {8, 8, 4, 4}, tryRaw[4] = {3, 2, 3, 2};
-    for (int i = 0; i < 4; i++) {
+    for (int i = (a.debugFlags & 16u) ? 2 : 0; i < 4; i++) {
         const size_t fixed = (size_t)tryA[i] * kGmATileBytes + (size_t)tryRaw[i] * kGmRawStageBytes;
         if (fixed + 2 * bTile > budget) continue;
         size_t nb = (budget - fixed) / bTile;

@@ -696,7 +696,7 @@ __device__ void megaAttention(const MegaArgs &m, const MegaSmem &sm, const MegaL
 }
 
 template <int HD>
-__global__ void __maxnreg__(112) megaDecodeKernel(const __grid_constant__ MegaArgs m) {
+__global__ void __launch_bounds__(kTmaThreads, 1) megaDecodeKernel(const __grid_constant__ MegaArgs m) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     MegaSmem sm;
