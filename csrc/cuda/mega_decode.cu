@@ -189,36 +189,16 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
                 }
             }
             float ss = 0.f;
-            if (IN_PLAIN) {
+            // NB: issuing the LL loads of several float4 before checking any epoch (one L2 round trip instead of one per value) was
+            // measured and rejected: the extra live registers push the 96-register kernel (17 warps are allocated as 20) into spilling
+            // inside the dp4a main loop (w13 main loop 8.0 -> 11.0 us per layer).
 #pragma unroll
-                for (int k = 0; k < kMaxVec; k++) {
-                    const uint32_t i = vecBase + k * kConsumerThreads + tid;
-                    xv[k] = i < nVec ? __ldcg(reinterpret_cast<const float4 *>(inF) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            } else {
-                // LL words: the loads of a group of two float4 (4 x 16 bytes) are issued before any epoch is checked — one L2 round trip
-                // per group instead of per value (a wider group spills: the 17-warp CTA is capped at 96 registers); a stale word
-                // falls back to the polling load
-                constexpr int G = 2;
-#pragma unroll
-                for (int k0 = 0; k0 < kMaxVec; k0 += G) {
-                    uint4 ra[G], rb[G];
-#pragma unroll
-                    for (int k = 0; k < G; k++) {
-                        const uint32_t i = vecBase + (k0 + k) * kConsumerThreads + tid;
-                        if (i < nVec) { ra[k] = ldW2(in + (size_t)i * 4); rb[k] = ldW2(in + (size_t)i * 4 + 2); }
-                    }
-#pragma unroll
-                    for (int k = 0; k < G; k++) {
-                        const uint32_t i = vecBase + (k0 + k) * kConsumerThreads + tid;
-                        if (i >= nVec) { xv[k0 + k] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
-                        if (ra[k].y != inEpoch || ra[k].w != inEpoch || rb[k].y != inEpoch || rb[k].w != inEpoch) xv[k0 + k] = ldW4wait(in, i, inEpoch, m.abortFlag);
-                        else xv[k0 + k] = make_float4(__uint_as_float(ra[k].x), __uint_as_float(ra[k].z), __uint_as_float(rb[k].x), __uint_as_float(rb[k].z));
-                    }
-                }
+            for (int k = 0; k < kMaxVec; k++) {
+                const uint32_t i = vecBase + k * kConsumerThreads + tid;
+                if (IN_PLAIN) xv[k] = i < nVec ? __ldcg(reinterpret_cast<const float4 *>(inF) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                else xv[k] = i < nVec ? ldW4wait(in, i, inEpoch, m.abortFlag) : make_float4(0.f, 0.f, 0.f, 0.f);
+                ss += xv[k].x * xv[k].x + xv[k].y * xv[k].y + xv[k].z * xv[k].z + xv[k].w * xv[k].w;
             }
-#pragma unroll
-            for (int k = 0; k < kMaxVec; k++) ss += xv[k].x * xv[k].x + xv[k].y * xv[k].y + xv[k].z * xv[k].z + xv[k].w * xv[k].w;
             float inv = 1.f;
             if (PRO == PRO_RMSNORM_) {
                 ss = consumerSum(ss, red);
