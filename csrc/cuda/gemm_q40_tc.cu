@@ -404,8 +404,14 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 if (grouped && tileTokens(item / splitK) == 0) continue;
                 const uint32_t tok0 = tileTok0(item / splitK);
                 for (uint32_t kb = kqBegin(ks) * 4; kb < min(kqBegin(ks + 1) * 4, nkb); kb++, it++) {
-                    const uint32_t s = it % a.bStages, ph = (it / a.bStages) & 1;
-                    gmBarWait(&bEmpty[s], ph ^ 1);
+                    const uint32_t s = it % a.bStages;
+                    // B stage s was last read by the MMAs of iteration it - bStages: their completion is already signalled on the A
+                    // ring (one tcgen05.commit per k-block; a second commit for a B-side barrier measurably slowed the MMA stream).
+                    // bStages <= stages, so that phase of emptyBar cannot have been overtaken yet.
+                    if (it >= a.bStages) {
+                        const uint32_t j = it - a.bStages;
+                        gmBarWait(&emptyBar[j % a.stages], (j / a.stages) & 1);
+                    }
                     gmBarExpectTx(&bFull[s], bTileBytes);
                     tmaLoad2d(bBase + (size_t)s * bTileBytes, &tmapB, kb * kGmBlockK, tok0, &bFull[s]);
                 }
@@ -436,7 +442,6 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
 #pragma unroll
                     for (uint32_t k = 0; k < kGmBlockK / 16; k++) umma(tmemD, descA + 2 * k, descB + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     ummaCommit(&emptyBar[s]);
-                    ummaCommit(&bEmpty[sb]);
                     if (kb == kb1 - 1) ummaCommit(&tmemFull[acc]);
                 }
                 __syncwarp();
@@ -739,7 +744,7 @@ static size_t tmaGeometry(GemmArgs &a) {
         const size_t fixed = (size_t)tryA[i] * kGmATileBytes + (size_t)tryRaw[i] * kGmRawStageBytes;
         if (fixed + 2 * bTile > budget) continue;
         size_t nb = (budget - fixed) / bTile;
-        if (nb > (size_t)kGmMaxStages) nb = kGmMaxStages;
+        if (nb > (size_t)tryA[i]) nb = tryA[i];      // the B ring is released through the A ring's barriers: never deeper than it
         a.stages = tryA[i]; a.rawStages = tryRaw[i]; a.bStages = (uint32_t)nb;
         return fixed + nb * bTile + 1024 + 512;
     }
@@ -804,7 +809,8 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
         const uint32_t nkq = n / 256;
         uint32_t sk = (uint32_t)numSms / nTilesM;
         if (sk > 8) sk = 8;
-        if (sk > nkq / 4) sk = nkq / 4;   // every split keeps >= 4 raw chunks (1024 of K)
+        if (nkq < 32) sk = 1;             // K < 8192 (qkv, wo): measured — the scratch round trip + last-arriver reduce costs more than the idle SMs
+        if (sk > nkq / 8) sk = nkq / 8;   // every split keeps >= 8 raw chunks (2048 of K)
         if (const char *f = getenv("DL_GEMM_SPLITK")) sk = (uint32_t)atoi(f) < 1 ? 1 : (uint32_t)atoi(f);
         if (sk >= 2) {
             const size_t need = (size_t)sk * T * d * sizeof(float);
