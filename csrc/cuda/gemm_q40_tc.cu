@@ -342,6 +342,9 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
     // work item -> (row tile, K range in 256-wide raw chunks); consecutive items share a tile
     auto kqBegin = [&](uint32_t ks) { return (uint32_t)(((uint64_t)ks * nkq) / splitK); };
     // grouped mode: (tile) -> weight row of the tile's first row, first activation/output row, number of valid tokens
+    // a.stages is 4 or 8 (tmaGeometry): stage / phase of the A ring by shift and mask; the raw and B rings (arbitrary depth) keep
+    // incremental (stage, parity) counters — a runtime `%` or `/` is a ~25-instruction I2F/MUFU.RCP sequence per use
+    const uint32_t aMask = a.stages - 1, aShift = a.stages == 8 ? 3u : 2u;
     const bool grouped = a.grpCount != nullptr;
     auto tileRow0 = [&](uint32_t tile) { return grouped ? (tile / a.grpTiles) * a.grpRows + (tile % a.grpTiles) * kGmBlockM : tile * kGmBlockM; };
     auto tileTokens = [&](uint32_t tile) { return grouped ? (uint32_t)__ldg(a.grpCount + tile / a.grpTiles) : a.T; };
@@ -379,18 +382,18 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
     if (warp == 3) {
         // ===================== raw weight producer (weights are constants: no dependency wait) =====================
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t rs = 0, ph = 0;
             for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
                 const uint32_t tile = item / splitK, ks = item - tile * splitK;
                 if (grouped && tileTokens(tile) == 0) continue;
                 const uint32_t wRow = tileRow0(tile);
-                for (uint32_t kq = kqBegin(ks); kq < kqBegin(ks + 1); kq++, it++) {
-                    const uint32_t rs = it % a.rawStages, ph = (it / a.rawStages) & 1;
+                for (uint32_t kq = kqBegin(ks); kq < kqBegin(ks + 1); kq++) {
                     gmBarWait(&rawEmpty[rs], ph ^ 1);
                     uint8_t *dst = rawBase + (size_t)rs * kGmRawStageBytes;
                     gmBarExpectTx(&rawFull[rs], kGmRawStageBytes);
                     tmaLoad2d(dst, &tmapQ, kq * 128, wRow, &rawFull[rs]);                 // nibbles: 128 B per row
                     tmaLoad2d(dst + kGmRawQsBytes, &tmapS, kq * 16, wRow, &rawFull[rs]);   // scales: 16 B per row
+                    if (++rs == a.rawStages) { rs = 0; ph ^= 1u; }
                 }
             }
         }
@@ -398,29 +401,30 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
         // ===================== activation producer =====================
         pdlWait();
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t it = 0, sbP = 0;
             for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
                 const uint32_t ks = item % splitK;
                 if (grouped && tileTokens(item / splitK) == 0) continue;
                 const uint32_t tok0 = tileTok0(item / splitK);
                 for (uint32_t kb = kqBegin(ks) * 4; kb < min(kqBegin(ks + 1) * 4, nkb); kb++, it++) {
-                    const uint32_t s = it % a.bStages;
+                    const uint32_t s = sbP;
                     // B stage s was last read by the MMAs of iteration it - bStages: their completion is already signalled on the A
                     // ring (one tcgen05.commit per k-block; a second commit for a B-side barrier measurably slowed the MMA stream).
                     // bStages <= stages, so that phase of emptyBar cannot have been overtaken yet.
                     if (it >= a.bStages) {
                         const uint32_t j = it - a.bStages;
-                        gmBarWait(&emptyBar[j % a.stages], (j / a.stages) & 1);
+                        gmBarWait(&emptyBar[j & aMask], (j >> aShift) & 1);
                     }
                     gmBarExpectTx(&bFull[s], bTileBytes);
                     tmaLoad2d(bBase + (size_t)s * bTileBytes, &tmapB, kb * kGmBlockK, tok0, &bFull[s]);
+                    if (++sbP == a.bStages) sbP = 0;
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((nTile >> 3) << 17) | ((uint32_t)(kGmBlockM >> 4) << 24);
-        uint32_t it = 0, tcount = 0;
+        uint32_t it = 0, tcount = 0, sbM = 0, phbM = 0;
         for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
             const uint32_t ks = item % splitK;
             if (grouped && tileTokens(item / splitK) == 0) continue;
@@ -431,8 +435,9 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             tcFenceAfter();
             const uint32_t tmemD = tmemBase + acc * nTile;
             for (uint32_t kb = kb0; kb < kb1; kb++, it++) {
-                const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
-                const uint32_t sb = it % a.bStages, phb = (it / a.bStages) & 1;
+                const uint32_t s = it & aMask, ph = (it >> aShift) & 1;
+                const uint32_t sb = sbM, phb = phbM;
+                if (++sbM == a.bStages) { sbM = 0; phbM ^= 1u; }
                 gmBarWait(&bFull[sb], phb);
                 gmBarWait(&fullBar[s], ph);
                 tcFenceAfter();
@@ -611,12 +616,13 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
         const uint32_t grp = (uint32_t)(warp - 8) >> 1;
         const uint32_t j = (uint32_t)tid - 256u - grp * 64u;       // 0..63: rows j and j + 64
         const __nv_bfloat162 off = __floats2bfloat162_rn(136.f, 136.f);
-        uint32_t itR = 0;
+        uint32_t itR = 0, rsD = 0, rphD = 0;
         for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
             const uint32_t ks = item % splitK;
             if (grouped && tileTokens(item / splitK) == 0) continue;
             for (uint32_t kq = kqBegin(ks); kq < kqBegin(ks + 1); kq++, itR++) {
-                const uint32_t rs = itR % a.rawStages, rph = (itR / a.rawStages) & 1;
+                const uint32_t rs = rsD, rph = rphD;
+                if (++rsD == a.rawStages) { rsD = 0; rphD ^= 1u; }
                 gmBarWait(&rawFull[rs], rph);
                 const uint8_t *rbase = rawBase + (size_t)rs * kGmRawStageBytes;
                 uint4 qv[2][2];
@@ -638,7 +644,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                     if (lane == 0) gmBarArrive(&rawEmpty[rs]);
                 }
                 const uint32_t itA = itR * 4 + grp;
-                const uint32_t s = itA % a.stages, ph = (itA / a.stages) & 1;
+                const uint32_t s = itA & aMask, ph = (itA >> aShift) & 1;
                 gmBarWait(&emptyBar[s], ph ^ 1);
                 uint8_t *aTile = smem + (size_t)s * kGmATileBytes;
 #pragma unroll
