@@ -62,6 +62,13 @@ __device__ __forceinline__ void apTmemLoad32(uint32_t taddr, uint32_t (&r)[32]) 
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// one lane of a converged warp; the predicate form keeps the enclosed tcgen05 operands in uniform registers
+__device__ __forceinline__ bool apElectOne() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(p));
+    return p != 0;
+}
+
 // Shared-memory matrix descriptors (sm_100 version 1, SWIZZLE_128B).
 //   K-major  : rows of 128 B (64 bf16 along K), 8-row groups 1024 B apart (SBO); LBO is fixed to 1 for swizzled K-major tiles.
 //   MN-major : rows of 128 B hold 64 consecutive M/N elements of ONE k index; 8 consecutive k rows form a 1024 B group (SBO);
@@ -100,7 +107,9 @@ __global__ void __launch_bounds__(kApThreads, 1) attnPrefillTcKernel(const __gri
              *sEmpty = bars + 11, *pFull = bars + 13, *pEmpty = bars + 14, *oFull = bars + 15;
     uint32_t *tmemBasePtr = reinterpret_cast<uint32_t *>(bars + 16);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp index via shuffle = warp-uniform for the compiler: the role branches become uniform control flow and the tcgen05 / TMA
+    // operands stay in uniform registers (with tid >> 5 every UTCHMMA sat in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop, ~100 clocks)
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t item = blockIdx.x;
     const uint32_t kvh = item / a.nQTiles, qt = item - kvh * a.nQTiles;
     const uint32_t t0 = qt * a.tq;
@@ -126,7 +135,7 @@ __global__ void __launch_bounds__(kApThreads, 1) attnPrefillTcKernel(const __gri
     apFenceBefore();
     __syncthreads();
     apFenceAfter();
-    const uint32_t tmemBase = *tmemBasePtr;
+    const uint32_t tmemBase = __shfl_sync(0xffffffffu, *tmemBasePtr, 0);
     const uint32_t tmemO = tmemBase + 256;             // S0: cols [0,128), S1: [128,256), O: [256, 256 + HD)
 
     if (warp == 0) {
@@ -161,7 +170,7 @@ __global__ void __launch_bounds__(kApThreads, 1) attnPrefillTcKernel(const __gri
             apBarWait(&kFull[st], ph);
             apBarWait(&sEmpty[sb], sph ^ 1);
             apFenceAfter();
-            if (lane == 0) {
+            if (apElectOne()) {
 #pragma unroll
                 for (uint32_t c = 0; c < NA; c++) {
                     const uint64_t dq = apDescK(apAddr(Qs + c * kApAtomBytes));
@@ -183,7 +192,7 @@ __global__ void __launch_bounds__(kApThreads, 1) attnPrefillTcKernel(const __gri
             apBarWait(pFull, j & 1);
             apBarWait(&vFull[vs], (j >> 1) & 1);
             apFenceAfter();
-            if (lane == 0) {
+            if (apElectOne()) {
 #pragma unroll
                 for (uint32_t kk = 0; kk < 8; kk++) {              // 8 slices of 16 KV positions
                     const uint64_t dp = apDescK(apAddr(Ps + (kk >> 2) * kApAtomBytes)) + 2 * (kk & 3);

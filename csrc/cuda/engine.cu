@@ -48,6 +48,7 @@ struct Engine {
     float **gatherUcDev = nullptr;
     unsigned int **flagUcDev = nullptr;
     uint32_t vocabLimit = 0;     // 0 = none; otherwise the greedy arg-max ignores vocabulary rows >= vocabLimit
+    bool prefillFusedAr = false; // TP prefill: GEMM + all-reduce in one kernel (DL_PREFILL_FUSED_AR=1) instead of GEMM, then all-reduce kernel
     bool tcAttn = true;          // prefill attention on tcgen05 (DL_NO_TC_ATTN=1: per-token CUDA-core kernel)
     bool fusedAttn = true, fusedArgmax = true, useTma = true;   // debugging switches (DL_NO_FUSED_ATTN / DL_NO_FUSED_ARGMAX / DL_NO_TMA)
 };
@@ -271,6 +272,7 @@ static int enginePrefill(Engine &e, uint32_t T, uint32_t p0, int wantLogits, cud
         fillAr(e, arP, 0);
         arP.slotStride = e.comm.prefillSlotStride;
         for (uint32_t r = 0; r < e.comm.nRanks; r++) arP.slots[r] = (uint64_t *)((uint8_t *)e.comm.arena[r] + e.comm.prefillSlotsOff);
+        arP.slotsMc = e.comm.mcArena ? (uint64_t *)((uint8_t *)e.comm.mcArena + e.comm.prefillSlotsOff) : nullptr;
     }
     DL_TRY(launchEmbedding(embTable(e), g.pTokens, g.px, c.dim, c.dim, g.vocabFull, (int)T, stream));
     for (uint32_t l = 0; l < c.nLayers; l++) {
@@ -299,7 +301,13 @@ static int enginePrefill(Engine &e, uint32_t T, uint32_t p0, int wantLogits, cud
             t.partial = g.pAttnPartial; t.counters = g.pAttnCounters; t.out = nullptr; t.outStride = qDim; t.outBf16 = (__nv_bfloat16 *)g.pzb;
             DL_TRY(launchAttnDecode(t, (int)T, stream, pdl));
         }
-        if (tp) { arP.parity = 0; DL_TRY(gemmQ40TcAr(L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, arP)); }
+        // tensor parallel: partial product into the (now free) qkv buffer with all SMs / split-K, then all-reduce + residual over
+        // peer memory as its own kernel (DL_PREFILL_FUSED_AR=1: the one-kernel GEMM + all-reduce epilogue instead)
+        if (tp && !e.prefillFusedAr) {
+            arP.parity = 0;
+            DL_TRY(gemmQ40Tc(GEPI_STORE_F32_, L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.pqkv, c.dim, c.numSms, stream, pdl));
+            DL_TRY(launchArResidual(g.px, g.pqkv, c.dim, T, arP, stream));
+        } else if (tp) { arP.parity = 0; DL_TRY(gemmQ40TcAr(L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, arP)); }
         else DL_TRY(gemmQ40Tc(GEPI_RESIDUAL_, L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, pdl));
         if (c.nExperts > 0) {
             // mixture of experts: route the whole chunk, sort the (token, expert) pairs, grouped tensor-core GEMMs, weighted combine
@@ -314,7 +322,11 @@ static int enginePrefill(Engine &e, uint32_t T, uint32_t p0, int wantLogits, cud
         }
         DL_TRY(launchRmsNormBf16(g.px, c.dim, L.norm1, g.pxn, c.dim, c.dim, c.eps, T, stream));
         DL_TRY(gemmQ40Tc(GEPI_SWIGLU_BF16_, L.w13Qs, L.w13Sc, 2 * c.ffDim, c.dim, g.pxn, c.dim, T, g.phb, c.ffDim, c.numSms, stream, pdl));
-        if (tp) { arP.parity = 1; DL_TRY(gemmQ40TcAr(L.w2Qs, L.w2Sc, c.dim, c.ffDim, g.phb, c.ffDim, T, g.px, c.dim, c.numSms, stream, arP)); }
+        if (tp && !e.prefillFusedAr) {
+            arP.parity = 1;
+            DL_TRY(gemmQ40Tc(GEPI_STORE_F32_, L.w2Qs, L.w2Sc, c.dim, c.ffDim, g.phb, c.ffDim, T, g.pqkv, c.dim, c.numSms, stream, pdl));
+            DL_TRY(launchArResidual(g.px, g.pqkv, c.dim, T, arP, stream));
+        } else if (tp) { arP.parity = 1; DL_TRY(gemmQ40TcAr(L.w2Qs, L.w2Sc, c.dim, c.ffDim, g.phb, c.ffDim, T, g.px, c.dim, c.numSms, stream, arP)); }
         else DL_TRY(gemmQ40Tc(GEPI_RESIDUAL_, L.w2Qs, L.w2Sc, c.dim, c.ffDim, g.phb, c.ffDim, T, g.px, c.dim, c.numSms, stream, pdl));
     }
     if (wantLogits) {
@@ -340,6 +352,7 @@ DL_EXPORT void *dl_engine_create(const dl::EngineConfig *cfg) {
     e->fusedArgmax = std::getenv("DL_NO_FUSED_ARGMAX") == nullptr;
     e->useTma = std::getenv("DL_NO_TMA") == nullptr;
     e->tcAttn = std::getenv("DL_NO_TC_ATTN") == nullptr;
+    e->prefillFusedAr = std::getenv("DL_PREFILL_FUSED_AR") != nullptr;
     if (e->cfg.numSms == 0) {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);

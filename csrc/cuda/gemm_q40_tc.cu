@@ -26,6 +26,10 @@ constexpr int kGmBlockK = 64;
 constexpr int kGmThreads = 512;
 constexpr int kGmDeqWarps = 8;
 constexpr int kGmMaxStages = 8;
+constexpr int kGmMaxBStages = 12;
+// DL_GEMM_DEBUG bit 9 (512): CTA 0 records %clock64 stamps of its pipeline events (tools/trace_gemm.py)
+__device__ unsigned long long gGemmTrace[4096];
+__device__ __forceinline__ unsigned long long gmClock() { unsigned long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }   // activation-tile ring of the TMA-staged variant
 constexpr int kGmATileBytes = kGmBlockM * kGmBlockK * 2;   // 16 KB
 
 enum { GEPI_STORE_F32 = 0, GEPI_RESIDUAL = 1, GEPI_SWIGLU_BF16 = 2, GEPI_STORE_BF16 = 3, GEPI_RESIDUAL_AR = 4 };
@@ -81,6 +85,12 @@ __device__ __forceinline__ void tmaLoad2d(void *dst, const CUtensorMap *map, uin
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(sAddr(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// one lane of a converged warp (elect.sync): the predicate form keeps the enclosed tcgen05 operands uniform
+__device__ __forceinline__ bool electOne() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void tcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
@@ -110,7 +120,11 @@ template <int EPI>
 __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcKernel(const __grid_constant__ CUtensorMap tmapB, GemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smemRaw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~(uintptr_t)1023);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so the role branches below are uniform control flow and
+    // the tcgen05 / TMA operands (descriptors, barrier addresses) stay in uniform registers. With `tid >> 5` every UTCHMMA / UTCBAR
+    // was wrapped in an ELECT + 5x R2UR.BROADCAST + BRA.U.ANY loop: ~100 clocks per instruction on the single MMA-issuing thread,
+    // which paced the whole k-loop (tools/trace_gemm.py: 480-650 clocks to issue 4 MMAs + 2 commits).
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t nTile = a.nTile;
     const uint32_t bTileBytes = nTile * 128;
     const uint32_t stageBytes = kGmATileBytes + bTileBytes;
@@ -143,7 +157,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcKernel(const __grid_co
     tcFenceBefore();
     __syncthreads();
     tcFenceAfter();
-    const uint32_t tmemBase = *tmemBasePtr;
+    const uint32_t tmemBase = __shfl_sync(0xffffffffu, *tmemBasePtr, 0);   // warp-uniform for the compiler
     pdlWait();   // activations (and the residual stream) come from the predecessor kernel
 
     if (warp == 0) {
@@ -172,10 +186,10 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcKernel(const __grid_co
                 const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
                 gmBarWait(&fullBar[s], ph);
                 tcFenceAfter();
-                if (lane == 0) {
-                    const uint32_t aAddr = sAddr(smem + (size_t)s * stageBytes);
-                    const uint64_t descA = makeSmemDesc(aAddr);
-                    const uint64_t descB = makeSmemDesc(aAddr + kGmATileBytes);
+                const uint32_t aAddr = sAddr(smem + (size_t)s * stageBytes);
+                const uint64_t descA = makeSmemDesc(aAddr);
+                const uint64_t descB = makeSmemDesc(aAddr + kGmATileBytes);
+                if (electOne()) {
 #pragma unroll
                     for (uint32_t k = 0; k < kGmBlockK / 16; k++)
                         umma(tmemD, descA + 2 * k, descB + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);   // +32 B per K=16 slice
@@ -304,7 +318,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcKernel(const __grid_co
 // [128 rows x 16 B] scales) into a 3-deep ring; the dequant warps read the chunk from shared memory. ~54 KB of weight
 // bytes are in flight per SM instead of the 16 KB the register-prefetching variant above can hold.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kGmRawStagesMax = 3;
+constexpr int kGmRawStagesMax = 8;
 constexpr int kGmRawK = 256;
 constexpr int kGmRawQsBytes = kGmBlockM * 128;               // 16 KB
 constexpr int kGmRawStageBytes = kGmRawQsBytes + kGmBlockM * 16;   // + 2 KB scales
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                                                                     const __grid_constant__ CUtensorMap tmapS, GemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smemRaw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~(uintptr_t)1023);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // see gemmQ40TcKernel
     const uint32_t nTile = a.nTile;
     const uint32_t bTileBytes = nTile * 128;
     // Two independent rings: A tiles (dequantised weights, written by the dequant warps) and B tiles (activations, TMA). Round 1
@@ -327,8 +341,8 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
     uint64_t *fullBar = reinterpret_cast<uint64_t *>(rawBase + (size_t)a.rawStages * kGmRawStageBytes);   // A tile converted
     uint64_t *emptyBar = fullBar + kGmMaxStages;                                                            // A tile consumed
     uint64_t *bFull = emptyBar + kGmMaxStages;
-    uint64_t *bEmpty = bFull + kGmMaxStages;
-    uint64_t *tmemFull = bEmpty + kGmMaxStages;
+    uint64_t *bEmpty = bFull + kGmMaxBStages;
+    uint64_t *tmemFull = bEmpty + kGmMaxBStages;
     uint64_t *tmemEmpty = tmemFull + 2;
     uint64_t *rawFull = tmemEmpty + 2;
     uint64_t *rawEmpty = rawFull + kGmRawStagesMax;
@@ -377,7 +391,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
     tcFenceBefore();
     __syncthreads();
     tcFenceAfter();
-    const uint32_t tmemBase = *tmemBasePtr;
+    const uint32_t tmemBase = __shfl_sync(0xffffffffu, *tmemBasePtr, 0);   // warp-uniform for the compiler
 
     if (warp == 3) {
         // ===================== raw weight producer (weights are constants: no dependency wait) =====================
@@ -391,8 +405,13 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                     gmBarWait(&rawEmpty[rs], ph ^ 1);
                     uint8_t *dst = rawBase + (size_t)rs * kGmRawStageBytes;
                     gmBarExpectTx(&rawFull[rs], kGmRawStageBytes);
+                    if (a.debugFlags & 256u) {   // timing experiment (wrong results): the same bytes as contiguous 16 KB + 2 KB blocks
+                        tmaLoad2d(dst, &tmapQ, 0, (tile * nkq + kq) * kGmBlockM, &rawFull[rs]);
+                        tmaLoad2d(dst + kGmRawQsBytes, &tmapS, 0, (tile * nkq + kq) * kGmBlockM, &rawFull[rs]);
+                    } else {
                     tmaLoad2d(dst, &tmapQ, kq * 128, wRow, &rawFull[rs]);                 // nibbles: 128 B per row
                     tmaLoad2d(dst + kGmRawQsBytes, &tmapS, kq * 16, wRow, &rawFull[rs]);   // scales: 16 B per row
+                    }
                     if (++rs == a.rawStages) { rs = 0; ph ^= 1u; }
                 }
             }
@@ -407,10 +426,10 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 if (grouped && tileTokens(item / splitK) == 0) continue;
                 const uint32_t tok0 = tileTok0(item / splitK);
                 for (uint32_t kb = kqBegin(ks) * 4; kb < min(kqBegin(ks + 1) * 4, nkb); kb++, it++) {
+                    // B stage s was last read by the MMAs of k-block it - bStages; their completion is already signalled on the A
+                    // ring's emptyBar (one tcgen05.commit per k-block: the issuing warp paces the k-loop, every instruction it
+                    // does not execute counts). bStages <= stages, so that phase of emptyBar cannot have been overtaken yet.
                     const uint32_t s = sbP;
-                    // B stage s was last read by the MMAs of iteration it - bStages: their completion is already signalled on the A
-                    // ring (one tcgen05.commit per k-block; a second commit for a B-side barrier measurably slowed the MMA stream).
-                    // bStages <= stages, so that phase of emptyBar cannot have been overtaken yet.
                     if (it >= a.bStages) {
                         const uint32_t j = it - a.bStages;
                         gmBarWait(&emptyBar[j & aMask], (j >> aShift) & 1);
@@ -423,8 +442,12 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // One k-block costs this warp ~650 clocks (two barrier probes of ~75 clocks, four UTCHMMA, two UTCBAR, ~100 instructions of
+        // descriptor / phase arithmetic) against 4 x 32 clocks of tensor-core work at N = 64: the k-loop is paced by this warp, not
+        // by the dequant groups or the rings (tools/trace_gemm.py). A second issuing warp (alternate k-blocks, own accumulator)
+        // hung the kernel on the first tile, see experiments/README.md.
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((nTile >> 3) << 17) | ((uint32_t)(kGmBlockM >> 4) << 24);
-        uint32_t it = 0, tcount = 0, sbM = 0, phbM = 0;
+        uint32_t itBase = 0, tcount = 0, sbM = 0, phbM = 0;
         for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
             const uint32_t ks = item % splitK;
             if (grouped && tileTokens(item / splitK) == 0) continue;
@@ -434,28 +457,38 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             gmBarWait(&tmemEmpty[acc], accPh ^ 1);
             tcFenceAfter();
             const uint32_t tmemD = tmemBase + acc * nTile;
-            for (uint32_t kb = kb0; kb < kb1; kb++, it++) {
+            for (uint32_t kb = kb0; kb < kb1; kb++) {
+                const uint32_t it = itBase + (kb - kb0);
                 const uint32_t s = it & aMask, ph = (it >> aShift) & 1;
                 const uint32_t sb = sbM, phb = phbM;
                 if (++sbM == a.bStages) { sbM = 0; phbM ^= 1u; }
+                const bool trc = (a.debugFlags & 512u) && blockIdx.x == 0 && lane == 0 && it < 256;
+                if (trc) gGemmTrace[it * 4 + 0] = gmClock();
                 gmBarWait(&bFull[sb], phb);
+                if (trc) gGemmTrace[it * 4 + 1] = gmClock();
                 gmBarWait(&fullBar[s], ph);
+                if (trc) gGemmTrace[it * 4 + 2] = gmClock();
                 tcFenceAfter();
-                if (lane == 0) {
-                    const uint64_t descA = makeSmemDesc(sAddr(smem + (size_t)s * kGmATileBytes));
-                    const uint64_t descB = makeSmemDesc(sAddr(bBase + (size_t)sb * bTileBytes));
+                const uint64_t descA = makeSmemDesc(sAddr(smem + (size_t)s * kGmATileBytes));
+                const uint64_t descB = makeSmemDesc(sAddr(bBase + (size_t)sb * bTileBytes));
+                if (electOne()) {
 #pragma unroll
-                    for (uint32_t k = 0; k < kGmBlockK / 16; k++) umma(tmemD, descA + 2 * k, descB + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                    for (uint32_t k = 0; k < kGmBlockK / 16; k++)
+                        if (!(a.debugFlags & 32u) || (kb == kb0 && k == 0)) umma(tmemD, descA + 2 * k, descB + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     ummaCommit(&emptyBar[s]);
                     if (kb == kb1 - 1) ummaCommit(&tmemFull[acc]);
                 }
+                if (trc) gGemmTrace[it * 4 + 3] = gmClock();
                 __syncwarp();
             }
+            itBase += kb1 - kb0;
         }
     } else if (warp >= 4 && warp < 8) {
         // ===================== epilogue =====================
         pdlWait();   // the residual stream is read-modify-written
         const uint32_t q = warp - 4;
+        // accumulator columns [c0, c0 + 16) of this warp's 32 rows
+        auto loadAcc = [&](uint32_t acc, uint32_t c0, uint32_t (&r)[16]) { tmemLoad16(tmemBase + ((q * 32u) << 16) + acc * nTile + c0, r); };
         uint32_t tcount = 0;
         for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
             const uint32_t tile = item / splitK, ks = item - tile * splitK;
@@ -474,7 +507,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 float *mineS = a.splitScratch + (size_t)ks * a.T * a.d;
                 for (uint32_t c0 = 0; c0 < nTile; c0 += 16) {
                     uint32_t r[16];
-                    tmemLoad16(tmemBase + ((q * 32u) << 16) + acc * nTile + c0, r);
+                    loadAcc(acc, c0, r);
 #pragma unroll
                     for (int j = 0; j < 16; j++)
                         if (c0 + j < a.T && fOk) mineS[(size_t)(c0 + j) * a.d + f] = __uint_as_float(r[j]);
@@ -529,7 +562,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 const size_t slotBase = (size_t)(ar.parity * ar.nRanks + ar.rank) * ar.slotStride;
                 for (uint32_t c0 = 0; c0 < nTile; c0 += 16) {
                     uint32_t r[16];
-                    tmemLoad16(tmemBase + ((q * 32u) << 16) + acc * nTile + c0, r);
+                    loadAcc(acc, c0, r);
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         const uint32_t tok = c0 + j;
@@ -587,7 +620,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                     for (int j = 0; j < 16; j++)
                         resid[j] = (c0 + j < Teff && fOk) ? __ldcg(reinterpret_cast<const float *>(a.out) + (size_t)(rowOff + c0 + j) * a.outStride + f) : 0.f;
                 }
-                tmemLoad16(tmemBase + ((q * 32u) << 16) + acc * nTile + c0, r);
+                loadAcc(acc, c0, r);
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     const uint32_t tok = c0 + j;
@@ -623,7 +656,11 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             for (uint32_t kq = kqBegin(ks); kq < kqBegin(ks + 1); kq++, itR++) {
                 const uint32_t rs = rsD, rph = rphD;
                 if (++rsD == a.rawStages) { rsD = 0; rphD ^= 1u; }
+                const bool trd = (a.debugFlags & 512u) && blockIdx.x == 0 && lane == 0 && !(warp & 1) && itR < 64;
+                unsigned long long *tq = gGemmTrace + 1024 + (grp * 64 + itR) * 8;
+                if (trd) tq[0] = gmClock();
                 gmBarWait(&rawFull[rs], rph);
+                if (trd) tq[1] = gmClock();
                 const uint8_t *rbase = rawBase + (size_t)rs * kGmRawStageBytes;
                 uint4 qv[2][2];
                 uint16_t sv[2][2];
@@ -645,10 +682,12 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 }
                 const uint32_t itA = itR * 4 + grp;
                 const uint32_t s = itA & aMask, ph = (itA >> aShift) & 1;
+                if (trd) tq[2] = gmClock();
                 gmBarWait(&emptyBar[s], ph ^ 1);
+                if (trd) tq[3] = gmClock();
                 uint8_t *aTile = smem + (size_t)s * kGmATileBytes;
 #pragma unroll
-                for (int rr = 0; rr < 2; rr++) {
+                for (int rr = 0; rr < 2 && !(a.debugFlags & 64u); rr++) {
                     const uint32_t row = j + 64 * rr;
                     const uint32_t swz = row & 7;
 #pragma unroll
@@ -671,8 +710,10 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                         }
                     }
                 }
+                if (trd) tq[4] = gmClock();
                 if (!(a.debugFlags & 1u)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
+                if (trd) tq[5] = gmClock();
                 if (lane == 0) {
                     gmBarArrive(&fullBar[s]);
                     if (lateRelease) gmBarArrive(&rawEmpty[rs]);
@@ -745,12 +786,21 @@ static bool encode2d(EncodeTiledFn enc, CUtensorMap *map, CUtensorMapDataType ty
 static size_t tmaGeometry(GemmArgs &a) {
     const size_t bTile = (size_t)a.nTile * 128;
     const size_t budget = 227 * 1024 - 1024 - 512;
-    const uint32_t tryA[4] = {8, 8, 4, 4}, tryRaw[4] = {3, 2, 3, 2};
-    for (int i = (a.debugFlags & 16u) ? 2 : 0; i < 4; i++) {
+    // Preference: the deeper A ring (two tiles per dequant group instead of one) with >= 4 activation tiles (measured: 2 costs
+    // ~15 %, more than 4 gains nothing), then three raw stages.
+    const uint32_t tryA[6] = {8, 8, 4, 4, 8, 4}, tryRaw[6] = {3, 2, 3, 2, 2, 2}, minB[6] = {4, 4, 4, 4, 2, 2};
+    if (const char *ea = getenv("DL_GEMM_GEOM")) {   // experiment: "A,raw,B" stage counts
+        unsigned ga = 0, gr = 0, gb = 0;
+        if (sscanf(ea, "%u,%u,%u", &ga, &gr, &gb) == 3 && (ga == 4 || ga == 8) && gr >= 2 && gr <= (unsigned)kGmRawStagesMax && gb >= 2 && gb <= ga) {
+            const size_t need = (size_t)ga * kGmATileBytes + (size_t)gr * kGmRawStageBytes + gb * bTile;
+            if (need <= budget) { a.stages = ga; a.rawStages = gr; a.bStages = gb; return need + 1024 + 512; }
+        }
+    }
+    for (int i = (a.debugFlags & 16u) ? 1 : 0; i < 6; i++) {
         const size_t fixed = (size_t)tryA[i] * kGmATileBytes + (size_t)tryRaw[i] * kGmRawStageBytes;
-        if (fixed + 2 * bTile > budget) continue;
+        if (fixed + minB[i] * bTile > budget) continue;
         size_t nb = (budget - fixed) / bTile;
-        if (nb > (size_t)tryA[i]) nb = tryA[i];      // the B ring is released through the A ring's barriers: never deeper than it
+        if (nb > 4) nb = 4;                           // more than 4 gains nothing; released through the A ring's barriers: never deeper than it
         a.stages = tryA[i]; a.rawStages = tryRaw[i]; a.bStages = (uint32_t)nb;
         return fixed + nb * bTile + 1024 + 512;
     }
@@ -805,8 +855,13 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
     if (!encode2d(enc, &mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, act, n, T, (uint64_t)actStride * 2, kGmBlockK, a.nTile, CU_TENSOR_MAP_SWIZZLE_128B))
         return -4;
     if (tma) {
+        if (a.debugFlags & 256u) {
+            if (!encode2d(enc, &mapQ, CU_TENSOR_MAP_DATA_TYPE_UINT8, qs, 128, (uint64_t)d * (n / 2) / 128, 128, 128, kGmBlockM, CU_TENSOR_MAP_SWIZZLE_128B)) return -7;
+            if (!encode2d(enc, &mapS, CU_TENSOR_MAP_DATA_TYPE_UINT8, scales, 16, (uint64_t)d * (n / 16) / 16, 16, 16, kGmBlockM, CU_TENSOR_MAP_SWIZZLE_NONE)) return -8;
+        } else {
         if (!encode2d(enc, &mapQ, CU_TENSOR_MAP_DATA_TYPE_UINT8, qs, n / 2, d, n / 2, 128, kGmBlockM, CU_TENSOR_MAP_SWIZZLE_128B)) return -7;
         if (!encode2d(enc, &mapS, CU_TENSOR_MAP_DATA_TYPE_UINT8, scales, n / 16, d, n / 16, 16, kGmBlockM, CU_TENSOR_MAP_SWIZZLE_NONE)) return -8;
+        }
     }
     const uint32_t nTilesM = (d + kGmBlockM - 1) / kGmBlockM;
     a.splitK = 1;
@@ -928,6 +983,10 @@ int launchRmsNormBf16(const float *x, uint32_t xStride, const float *w, void *y,
 }
 
 }  // namespace dl
+
+DL_EXPORT int dl_gemm_trace_read(unsigned long long *host) {
+    return (int)cudaMemcpyFromSymbol(host, dl::gGemmTrace, sizeof(unsigned long long) * 4096);
+}
 
 DL_EXPORT int dl_gemm_q40_tc(int epi, const void *qs, const void *scales, uint32_t d, uint32_t n, const void *act, uint32_t actStride,
                              uint32_t T, void *out, uint32_t outStride, int numSms, cudaStream_t stream, int pdl, int variant) {

@@ -225,6 +225,7 @@ struct MoePrefillArgs {
     ArArgs ar;                    // nRanks > 1: partial sums are all-reduced over peer memory inside the combine kernel
 };
 int moePrefillFfn(const MoePrefillArgs &a, cudaStream_t stream);   // 1: shape not covered
+int launchArResidual(float *x, const float *partial, uint32_t dim, uint32_t T, const ArArgs &ar, cudaStream_t stream);   // x += all-reduce(partial)
 int launchRmsNormBf16(const float *x, uint32_t xStride, const float *w, void *y, uint32_t yStride, uint32_t n, float eps, uint32_t T,
                       cudaStream_t stream);
 

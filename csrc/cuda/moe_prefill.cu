@@ -99,6 +99,36 @@ __global__ void __launch_bounds__(256) moeCombineKernel(float *x, uint32_t dim, 
     x[(size_t)t * dim + f] += acc;
 }
 
+// x[t][f] += sum over ranks of partial_r[t][f]: the tensor-parallel all-reduce + residual of a prompt chunk as its own kernel, so
+// that the producing GEMM keeps split-K and all SMs (the fused GEMM + all-reduce epilogue pins one CTA per 128-row tile while it
+// polls). Push: one multimem.st per cell through the NVSwitch multicast mapping (or nRanks unicast stores); pull: the N source
+// slots of the cell, summed in rank order.
+__global__ void __launch_bounds__(256) arResidualKernel(float *x, const float *__restrict__ partial, uint32_t dim, uint32_t T, ArArgs ar) {
+    const uint32_t t = blockIdx.y;
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= dim || t >= T) return;
+    const float mineV = partial[(size_t)t * dim + f];
+    const size_t cell = (size_t)t * ar.dim + f;
+    const size_t mineOff = (size_t)(ar.parity * ar.nRanks + ar.rank) * ar.slotStride + cell;
+    if (ar.slotsMc) {
+        const uint64_t word = (uint64_t)__float_as_uint(mineV) | (1ull << 32);
+        asm volatile("multimem.st.relaxed.sys.global.b64 [%0], %1;" ::"l"(ar.slotsMc + mineOff), "l"(word) : "memory");
+    } else {
+        for (uint32_t p = 0; p < ar.nRanks; p++) stLL(ar.slots[(ar.rank + p) % ar.nRanks] + mineOff, __float_as_uint(mineV), 1u);
+    }
+    float sum = 0.f;
+    uint64_t *mine = ar.slots[ar.rank];
+    for (uint32_t sr = 0; sr < ar.nRanks; sr++) {
+        uint64_t *w = mine + (size_t)(ar.parity * ar.nRanks + sr) * ar.slotStride + cell;
+        uint2 v = ldLL(w);
+        uint32_t spins = 0;
+        while (v.y == 0u && ++spins < (1u << 28)) v = ldLL(w);
+        sum += __uint_as_float(v.x);
+        stLL(w, 0u, 0u);
+    }
+    x[(size_t)t * dim + f] += sum;
+}
+
 struct MoeScratch {
     int *count = nullptr, *offset = nullptr, *slotOfPair = nullptr, *tokenOfSlot = nullptr, *totalRows = nullptr;
     int *expertIdx = nullptr;
@@ -132,6 +162,12 @@ int moeEnsureScratch(uint32_t nPairs, uint32_t dim, uint32_t ff, uint32_t nExper
 }
 
 }  // namespace
+
+int launchArResidual(float *x, const float *partial, uint32_t dim, uint32_t T, const ArArgs &ar, cudaStream_t stream) {
+    arResidualKernel<<<dim3((dim + 255) / 256, T), 256, 0, stream>>>(x, partial, dim, T, ar);
+    DL_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
 
 // MoE feed-forward of a prompt chunk: x [T][dim] f32 (residual stream, updated in place), xnScratch bf16 [T][dim].
 // w13: [nLocal][2*ff][dim] gate/up interleaved, w2: [nLocal][dim][ff]. Returns 1 when the shape is not covered by the grouped GEMM.

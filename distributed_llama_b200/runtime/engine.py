@@ -74,7 +74,7 @@ class Engine:
         self.p_tokens = torch.zeros(mp, dtype=torch.int32, device=dev)
         self.p_pos = torch.zeros(mp, dtype=torch.int32, device=dev)
         self.p_x = torch.zeros(mp, h.dim, **f32)
-        self.p_qkv = torch.zeros(mp, self.qkv_dim, **f32)
+        self.p_qkv = torch.zeros(mp, max(self.qkv_dim, h.dim), **f32)   # also the [T][dim] partial of the TP WO / W2 GEMMs
         self.p_xn = torch.zeros(mp, h.dim, **bf16)
         self.p_zb = torch.zeros(mp, q_dim, **bf16)
         self.p_hb = torch.zeros(mp, w.ff_dim, **bf16)
