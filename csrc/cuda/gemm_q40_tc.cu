@@ -42,7 +42,8 @@ struct GemmArgs {
     void *out;
     uint32_t outStride;   // elements between tokens
     uint32_t stages, tmemCols;
-    uint32_t bStages;      // TMA-staged variant: depth of the activation-tile ring (decoupled from the A-tile ring)
+    uint32_t bStages;      // TMA-staged variant: depth of the activation-tile ring (decoupled from the A-tile ring), in MMA steps
+    uint32_t kPair;        // TMA-staged variant: 64-wide k-blocks per MMA step (1 or 2): one barrier round + one commit per step
     uint32_t splitK;       // TMA-staged variant: K is cut into splitK ranges handled by different CTAs (work item = tile x split)
     float *splitScratch;   // [splitK][T][d] f32 partial accumulators
     unsigned int *splitCounters;   // [nTilesM * 4], zero-initialised, self-resetting (one per 32-row quarter of a tile)
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
     // wait for the MMA of its previous tile before converting the next (ncu: dequant warps 50 % in long-scoreboard waits, tensor
     // pipe 10 %). Now the A ring is 8 deep (2 per group) whatever the token count.
     uint8_t *bBase = smem + (size_t)a.stages * kGmATileBytes;
-    uint8_t *rawBase = bBase + (size_t)a.bStages * bTileBytes;        // [rawStages][18 KB], 1024-aligned (all tiles are multiples of 1 KB)
+    uint8_t *rawBase = bBase + (size_t)a.bStages * a.kPair * bTileBytes;        // [rawStages][18 KB], 1024-aligned (all tiles are multiples of 1 KB)
     uint64_t *fullBar = reinterpret_cast<uint64_t *>(rawBase + (size_t)a.rawStages * kGmRawStageBytes);   // A tile converted
     uint64_t *emptyBar = fullBar + kGmMaxStages;                                                            // A tile consumed
     uint64_t *bFull = emptyBar + kGmMaxStages;
@@ -359,6 +360,9 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
     // a.stages is 4 or 8 (tmaGeometry): stage / phase of the A ring by shift and mask; the raw and B rings (arbitrary depth) keep
     // incremental (stage, parity) counters — a runtime `%` or `/` is a ~25-instruction I2F/MUFU.RCP sequence per use
     const uint32_t aMask = a.stages - 1, aShift = a.stages == 8 ? 3u : 2u;
+    // MMA step = kPair adjacent k-slices (A-ring slots 2p, 2p+1 are adjacent in shared memory) sharing one full / empty barrier
+    // pair, indexed by slot >> pShift; the phase of a slot and of its step are the same bit of the slice counter.
+    const uint32_t pShift = a.kPair == 2 ? 1u : 0u;
     const bool grouped = a.grpCount != nullptr;
     auto tileRow0 = [&](uint32_t tile) { return grouped ? (tile / a.grpTiles) * a.grpRows + (tile % a.grpTiles) * kGmBlockM : tile * kGmBlockM; };
     auto tileTokens = [&](uint32_t tile) { return grouped ? (uint32_t)__ldg(a.grpCount + tile / a.grpTiles) : a.T; };
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
     pdlLaunchDependents();
     if (tid == 0) {
         for (uint32_t s = 0; s < a.stages; s++) {
-            gmBarInit(&fullBar[s], 2);       // the two dequant warps that own this k-slice
+            gmBarInit(&fullBar[s], 2 * a.kPair);   // the dequant warps that fill the step's k-slices (indexed by step slot: s < stages / kPair used)
             gmBarInit(&emptyBar[s], 1);
         }
         for (uint32_t s = 0; s < a.bStages; s++) {
@@ -425,17 +429,18 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 const uint32_t ks = item % splitK;
                 if (grouped && tileTokens(item / splitK) == 0) continue;
                 const uint32_t tok0 = tileTok0(item / splitK);
-                for (uint32_t kb = kqBegin(ks) * 4; kb < min(kqBegin(ks + 1) * 4, nkb); kb++, it++) {
-                    // B stage s was last read by the MMAs of k-block it - bStages; their completion is already signalled on the A
-                    // ring's emptyBar (one tcgen05.commit per k-block: the issuing warp paces the k-loop, every instruction it
-                    // does not execute counts). bStages <= stages, so that phase of emptyBar cannot have been overtaken yet.
+                for (uint32_t kb = kqBegin(ks) * 4; kb < min(kqBegin(ks + 1) * 4, nkb); kb += a.kPair, it++) {
+                    // `it` counts MMA steps. B stage s was last read by the MMAs of step it - bStages; their completion is already
+                    // signalled on the A ring's emptyBar (one tcgen05.commit per step: the issuing warp paces the k-loop, every
+                    // instruction it does not execute counts). bStages <= stages / kPair, so that phase cannot have been overtaken.
                     const uint32_t s = sbP;
                     if (it >= a.bStages) {
-                        const uint32_t j = it - a.bStages;
-                        gmBarWait(&emptyBar[j & aMask], (j >> aShift) & 1);
+                        const uint32_t j = (it - a.bStages) << pShift;      // first k-slice of that step
+                        gmBarWait(&emptyBar[(j & aMask) >> pShift], (j >> aShift) & 1);
                     }
-                    gmBarExpectTx(&bFull[s], bTileBytes);
-                    tmaLoad2d(bBase + (size_t)s * bTileBytes, &tmapB, kb * kGmBlockK, tok0, &bFull[s]);
+                    gmBarExpectTx(&bFull[s], bTileBytes * a.kPair);
+                    for (uint32_t h = 0; h < a.kPair; h++)
+                        tmaLoad2d(bBase + ((size_t)s * a.kPair + h) * bTileBytes, &tmapB, (kb + h) * kGmBlockK, tok0, &bFull[s]);
                     if (++sbP == a.bStages) sbP = 0;
                 }
             }
@@ -457,8 +462,8 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             gmBarWait(&tmemEmpty[acc], accPh ^ 1);
             tcFenceAfter();
             const uint32_t tmemD = tmemBase + acc * nTile;
-            for (uint32_t kb = kb0; kb < kb1; kb++) {
-                const uint32_t it = itBase + (kb - kb0);
+            for (uint32_t kb = kb0; kb < kb1; kb += a.kPair) {
+                const uint32_t it = itBase + (kb - kb0);                 // k-slice counter of the step's first slice
                 const uint32_t s = it & aMask, ph = (it >> aShift) & 1;
                 const uint32_t sb = sbM, phb = phbM;
                 if (++sbM == a.bStages) { sbM = 0; phbM ^= 1u; }
@@ -466,17 +471,23 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 if (trc) gGemmTrace[it * 4 + 0] = gmClock();
                 gmBarWait(&bFull[sb], phb);
                 if (trc) gGemmTrace[it * 4 + 1] = gmClock();
-                gmBarWait(&fullBar[s], ph);
+                gmBarWait(&fullBar[s >> pShift], ph);
                 if (trc) gGemmTrace[it * 4 + 2] = gmClock();
                 tcFenceAfter();
                 const uint64_t descA = makeSmemDesc(sAddr(smem + (size_t)s * kGmATileBytes));
-                const uint64_t descB = makeSmemDesc(sAddr(bBase + (size_t)sb * bTileBytes));
+                const uint64_t descB = makeSmemDesc(sAddr(bBase + (size_t)sb * a.kPair * bTileBytes));
                 if (electOne()) {
 #pragma unroll
                     for (uint32_t k = 0; k < kGmBlockK / 16; k++)
                         if (!(a.debugFlags & 32u) || (kb == kb0 && k == 0)) umma(tmemD, descA + 2 * k, descB + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-                    ummaCommit(&emptyBar[s]);
-                    if (kb == kb1 - 1) ummaCommit(&tmemFull[acc]);
+                    if (a.kPair == 2) {
+                        // second k-slice of the step: next A slot (+16 KB) and the second half of the B stage (descriptor address units: 16 B)
+                        const uint64_t descA2 = descA + (kGmATileBytes >> 4), descB2 = descB + (bTileBytes >> 4);
+#pragma unroll
+                        for (uint32_t k = 0; k < kGmBlockK / 16; k++) umma(tmemD, descA2 + 2 * k, descB2 + 2 * k, idesc, 1u);
+                    }
+                    ummaCommit(&emptyBar[s >> pShift]);
+                    if (kb + a.kPair >= kb1) ummaCommit(&tmemFull[acc]);
                 }
                 if (trc) gGemmTrace[it * 4 + 3] = gmClock();
                 __syncwarp();
@@ -649,6 +660,8 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
         const uint32_t grp = (uint32_t)(warp - 8) >> 1;
         const uint32_t j = (uint32_t)tid - 256u - grp * 64u;       // 0..63: rows j and j + 64
         const __nv_bfloat162 off = __floats2bfloat162_rn(136.f, 136.f);
+        uint32_t nibMask = 0x000f000fu, bfMagic = 0x43004300u;
+        asm volatile("" : "+r"(nibMask), "+r"(bfMagic));   // opaque: keeps both constants in registers
         uint32_t itR = 0, rsD = 0, rphD = 0;
         for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
             const uint32_t ks = item % splitK;
@@ -683,7 +696,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 const uint32_t itA = itR * 4 + grp;
                 const uint32_t s = itA & aMask, ph = (itA >> aShift) & 1;
                 if (trd) tq[2] = gmClock();
-                gmBarWait(&emptyBar[s], ph ^ 1);
+                gmBarWait(&emptyBar[s >> pShift], ph ^ 1);
                 if (trd) tq[3] = gmClock();
                 uint8_t *aTile = smem + (size_t)s * kGmATileBytes;
 #pragma unroll
@@ -700,7 +713,10 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                             uint32_t o[4];
 #pragma unroll
                             for (int sft = 0; sft < 4; sft++) {
-                                uint32_t t = ((w[c] >> (4 * sft)) & 0x000f000fu) | 0x43004300u;
+                                // (x & 0x000f000f) | 0x43004300 as ONE lop3 (both constants in registers; with immediates the
+                                // compiler emits two LOP3 per pair: the conversion is issue-bound, ~4.75 -> 3.75 instructions per pair)
+                                uint32_t t;
+                                asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(t) : "r"(w[c] >> (4 * sft)), "r"(nibMask), "r"(bfMagic));
                                 __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162 *>(&t);
                                 v = __hmul2(__hsub2(v, off), sc2);
                                 o[sft] = *reinterpret_cast<uint32_t *>(&v);
@@ -715,7 +731,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 __syncwarp();
                 if (trd) tq[5] = gmClock();
                 if (lane == 0) {
-                    gmBarArrive(&fullBar[s]);
+                    gmBarArrive(&fullBar[s >> pShift]);
                     if (lateRelease) gmBarArrive(&rawEmpty[rs]);
                 }
             }
@@ -786,23 +802,28 @@ static bool encode2d(EncodeTiledFn enc, CUtensorMap *map, CUtensorMapDataType ty
 static size_t tmaGeometry(GemmArgs &a) {
     const size_t bTile = (size_t)a.nTile * 128;
     const size_t budget = 227 * 1024 - 1024 - 512;
-    // Preference: the deeper A ring (two tiles per dequant group instead of one) with >= 4 activation tiles (measured: 2 costs
-    // ~15 %, more than 4 gains nothing), then three raw stages.
-    const uint32_t tryA[6] = {8, 8, 4, 4, 8, 4}, tryRaw[6] = {3, 2, 3, 2, 2, 2}, minB[6] = {4, 4, 4, 4, 2, 2};
-    if (const char *ea = getenv("DL_GEMM_GEOM")) {   // experiment: "A,raw,B" stage counts
-        unsigned ga = 0, gr = 0, gb = 0;
-        if (sscanf(ea, "%u,%u,%u", &ga, &gr, &gb) == 3 && (ga == 4 || ga == 8) && gr >= 2 && gr <= (unsigned)kGmRawStagesMax && gb >= 2 && gb <= ga) {
-            const size_t need = (size_t)ga * kGmATileBytes + (size_t)gr * kGmRawStageBytes + gb * bTile;
-            if (need <= budget) { a.stages = ga; a.rawStages = gr; a.bStages = gb; return need + 1024 + 512; }
+    // Candidates in order of preference: {k-slices per MMA step, A slices, raw stages, minimum B steps}. Two slices per step halve the
+    // barrier probes / commits of the issuing warp (it paces the k-loop at <= 128 tokens); then the deeper A ring (two slices per
+    // dequant group), then >= 4 k-slices of activations in flight (2 measured ~15 % slower, more than 4 gains nothing).
+    static const uint32_t cand[9][4] = {{2, 8, 3, 2}, {2, 8, 2, 2}, {2, 4, 3, 2}, {1, 8, 3, 4}, {1, 8, 2, 4}, {1, 4, 3, 4}, {1, 4, 2, 4}, {1, 8, 2, 2}, {1, 4, 2, 2}};
+    if (const char *ea = getenv("DL_GEMM_GEOM")) {   // experiment: "kPair,A,raw,B"
+        unsigned gp = 0, ga = 0, gr = 0, gb = 0;
+        if (sscanf(ea, "%u,%u,%u,%u", &gp, &ga, &gr, &gb) == 4 && (gp == 1 || gp == 2) && (ga == 4 || ga == 8) && gr >= 2 && gr <= (unsigned)kGmRawStagesMax &&
+            gb >= 2 && gb <= ga / gp) {
+            const size_t need = (size_t)ga * kGmATileBytes + (size_t)gr * kGmRawStageBytes + gb * gp * bTile;
+            if (need <= budget) { a.kPair = gp; a.stages = ga; a.rawStages = gr; a.bStages = gb; return need + 1024 + 512; }
         }
     }
-    for (int i = (a.debugFlags & 16u) ? 1 : 0; i < 6; i++) {
-        const size_t fixed = (size_t)tryA[i] * kGmATileBytes + (size_t)tryRaw[i] * kGmRawStageBytes;
-        if (fixed + minB[i] * bTile > budget) continue;
-        size_t nb = (budget - fixed) / bTile;
-        if (nb > 4) nb = 4;                           // more than 4 gains nothing; released through the A ring's barriers: never deeper than it
-        a.stages = tryA[i]; a.rawStages = tryRaw[i]; a.bStages = (uint32_t)nb;
-        return fixed + nb * bTile + 1024 + 512;
+    for (int i = 0; i < 9; i++) {
+        const uint32_t kp = cand[i][0], nA = cand[i][1], nRaw = cand[i][2], minB = cand[i][3];
+        if (kp == 2 && (a.debugFlags & 16u)) continue;
+        const size_t fixed = (size_t)nA * kGmATileBytes + (size_t)nRaw * kGmRawStageBytes, bStage = kp * bTile;
+        if (fixed + minB * bStage > budget) continue;
+        size_t nb = (budget - fixed) / bStage;
+        const size_t cap = kp == 2 ? nA / 2 : 4;      // released through the A ring's barriers: never deeper than it (in steps)
+        if (nb > cap) nb = cap;
+        a.kPair = kp; a.stages = nA; a.rawStages = nRaw; a.bStages = (uint32_t)nb;
+        return fixed + nb * bStage + 1024 + 512;
     }
     return 0;
 }
