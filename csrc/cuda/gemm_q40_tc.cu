@@ -46,7 +46,7 @@ struct GemmArgs {
     uint32_t kPair;        // TMA-staged variant: 64-wide k-blocks per MMA step (1 or 2): one barrier round + one commit per step
     uint32_t splitK;       // TMA-staged variant: K is cut into splitK ranges handled by different CTAs (work item = tile x split)
     float *splitScratch;   // [splitK][T][d] f32 partial accumulators
-    unsigned int *splitCounters;   // [nTilesM * 4], zero-initialised, self-resetting (one per 32-row quarter of a tile)
+    unsigned int *splitCounters;   // [nTilesM * 4][2], zero-initialised, self-resetting (arrived / done, per 32-row quarter of a tile)
     ArArgs ar;             // GEPI_RESIDUAL_AR: tensor-parallel all-reduce fused into the epilogue (LL words over peer memory)
     uint32_t rawStages;    // TMA-staged variant: depth of the raw q40 ring (2 or 3)
     uint32_t debugFlags;   // bit0: skip the proxy fence, bit1: skip the A-tile stores (timing experiments only)
@@ -514,7 +514,10 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             const bool fOk = f < (grouped ? a.grpRows : a.d);
             const uint32_t rowOff = tileTok0(tile);
             if (splitK > 1) {
-                // ---- split-K: park the partial accumulator, the last split of this 32-row quarter reduces in fixed order ----
+                // ---- split-K: park the partial accumulator; once all splits of this 32-row quarter have arrived, every split reduces
+                // its own share of the tokens (fixed summation order -> deterministic). All splits of a tile are co-resident (one item
+                // per CTA, nItems <= SMs), so the wait cannot deadlock; the reduce is latency-bound (a dependent L2 round trip per
+                // round of 8 tokens), which is why it is spread over the splits instead of left to the last arriver.
                 float *mineS = a.splitScratch + (size_t)ks * a.T * a.d;
                 for (uint32_t c0 = 0; c0 < nTile; c0 += 16) {
                     uint32_t r[16];
@@ -528,39 +531,49 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
                 if (lane == 0) gmBarArrive(&tmemEmpty[acc]);
                 __threadfence();
                 __syncwarp();
-                unsigned int prev = 0;
-                if (lane == 0) prev = atomicAdd(&a.splitCounters[tile * 4 + q], 1u);
-                prev = __shfl_sync(0xffffffffu, prev, 0);
-                if (prev != splitK - 1) continue;
-                if (lane == 0) a.splitCounters[tile * 4 + q] = 0;
-                __threadfence();
-                for (uint32_t tok0 = 0; tok0 < a.T; tok0 += 4) {
-                    // 4 tokens x up to 8 splits (+ 4 residual values) are loaded before any arithmetic: ~36 loads in flight per thread
-                    float part[4][8], res[4];
+                unsigned int *ctr = a.splitCounters + (size_t)(tile * 4 + q) * 2;   // [0]: splits arrived, [1]: splits done reducing
+                if (lane == 0) {
+                    atomicAdd(ctr, 1u);
+                    unsigned int seen = 0, spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+                        if (seen < splitK) __nanosleep(64);
+                    } while (seen < splitK && ++spins < (1u << 24));
+                }
+                __syncwarp();
+                const uint32_t per = (a.T + splitK - 1) / splitK, tBeg = ks * per, tEnd = min(a.T, tBeg + per);
+                for (uint32_t tok0 = tBeg; tok0 < tEnd; tok0 += 8) {
+                    // 8 tokens x up to 4 splits (+ 8 residual values) are loaded before any arithmetic: ~40 loads in flight per thread
+                    float part[8][4], res[8];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const bool ok = fOk && tok0 + j < a.T;
+                    for (int j = 0; j < 8; j++) {
+                        const bool ok = fOk && tok0 + j < tEnd;
 #pragma unroll
-                        for (int k2 = 0; k2 < 8; k2++)
+                        for (int k2 = 0; k2 < 4; k2++)
                             part[j][k2] = (ok && (uint32_t)k2 < splitK) ? __ldcg(a.splitScratch + ((size_t)k2 * a.T + tok0 + j) * a.d + f) : 0.f;
                         res[j] = (EPI == GEPI_RESIDUAL && ok) ? __ldcg(reinterpret_cast<const float *>(a.out) + (size_t)(tok0 + j) * a.outStride + f) : 0.f;
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
+                    for (int j = 0; j < 8; j++) {
                         const uint32_t tok = tok0 + j;
                         float v = 0.f;
 #pragma unroll
-                        for (int k2 = 0; k2 < 8; k2++) v += part[j][k2];          // fixed order -> deterministic
+                        for (int k2 = 0; k2 < 4; k2++) v += part[j][k2];          // fixed order -> deterministic
                         if (EPI == GEPI_SWIGLU_BF16) {
                             const float other = __shfl_xor_sync(0xffffffffu, v, 1);
-                            if (fOk && tok < a.T && !(lane & 1))
+                            if (fOk && tok < tEnd && !(lane & 1))
                                 reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(gateAct(v, a.act) * other);
-                        } else if (fOk && tok < a.T) {
+                        } else if (fOk && tok < tEnd) {
                             if (EPI == GEPI_STORE_F32) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v;
                             if (EPI == GEPI_RESIDUAL) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = res[j] + v;
                             if (EPI == GEPI_STORE_BF16) reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + f] = __float2bfloat16_rn(v);
                         }
                     }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    // the split that finishes last re-arms the counters for the next launch (everyone has passed the wait by then)
+                    if (atomicAdd(ctr + 1, 1u) == splitK - 1) { ctr[0] = 0; ctr[1] = 0; }
                 }
                 continue;
             }
@@ -890,10 +903,13 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
         // small-d matrices (qkv, wo, w2) leave most SMs idle with one CTA per 128-row tile: cut K so that ~all SMs get an item
         const uint32_t nkq = n / 256;
         uint32_t sk = (uint32_t)numSms / nTilesM;
-        if (sk > 8) sk = 8;
-        if (nkq < 32) sk = 1;             // K < 8192 (qkv, wo): measured — the scratch round trip + last-arriver reduce costs more than the idle SMs
-        if (sk > nkq / 8) sk = nkq / 8;   // every split keeps >= 8 raw chunks (2048 of K)
-        if (const char *f = getenv("DL_GEMM_SPLITK")) sk = (uint32_t)atoi(f) < 1 ? 1 : (uint32_t)atoi(f);
+        // The k-loop of one CTA is latency-bound (~290 ns per 64 of K whatever the number of busy SMs), so idle SMs are worth a
+        // split even at K = 4096; the cooperative reduce costs a few us. At most 4 splits (reduce register budget), every split
+        // keeps >= 4 raw chunks (1024 of K), and all items must be co-resident (the reduce waits for its sibling splits).
+        if (sk > 4) sk = 4;
+        if (sk > nkq / 4) sk = nkq / 4;
+        if (nkq < 32 && sk < 4) sk = 1;   // K < 8192: measured at d = 6144 (48 tiles, 3 splits) — the reduce (~6-10 us) eats the shorter k-loop
+        if (const char *f = getenv("DL_GEMM_SPLITK")) { const uint32_t want = (uint32_t)atoi(f); if (want >= 1 && want < sk) sk = want; }
         if (sk >= 2) {
             const size_t need = (size_t)sk * T * d * sizeof(float);
             if (need > gSplitScratchBytes) {
@@ -905,7 +921,7 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
                 DL_CUDA_CHECK(cudaMalloc(&gSplitCounters, 4096 * sizeof(unsigned int)));
                 DL_CUDA_CHECK(cudaMemset(gSplitCounters, 0, 4096 * sizeof(unsigned int)));
             }
-            if (nTilesM * 4 <= 4096) { a.splitK = sk; a.splitScratch = gSplitScratch; a.splitCounters = gSplitCounters; }
+            if (nTilesM * 8 <= 4096) { a.splitK = sk; a.splitScratch = gSplitScratch; a.splitCounters = gSplitCounters; }
         }
     }
     const uint32_t nItems = nTilesM * a.splitK;
