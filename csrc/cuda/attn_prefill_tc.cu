@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(kApThreads, 1) attnPrefillTcKernel(const __gri
     const uint32_t nKv = (a.p0 + t0 + tqValid + 127) / 128;      // KV tiles this query tile can see
     const uint32_t kvRow0 = kvh * a.seqLen;
 
+    pdlLaunchDependents();
     if (tid == 0) {
         apBarInit(qReady, 4);
         for (int i = 0; i < 2; i++) {
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(kApThreads, 1) attnPrefillTcKernel(const __gri
     apFenceBefore();
     __syncthreads();
     apFenceAfter();
+    pdlWait();   // q rows and the new K/V rows come from the rope kernel before this one
     const uint32_t tmemBase = __shfl_sync(0xffffffffu, *tmemBasePtr, 0);
     const uint32_t tmemO = tmemBase + 256;             // S0: cols [0,128), S1: [128,256), O: [256, 256 + HD)
 
@@ -364,14 +366,14 @@ bool apCacheMap(CUtensorMap *map, const void *cache, uint32_t hd, uint64_t rows)
 }
 
 template <int HD>
-int apLaunch(const CUtensorMap &mk, const CUtensorMap &mv, const AttnPrefillKArgs &k, uint32_t grid, cudaStream_t stream) {
+int apLaunch(const CUtensorMap &mk, const CUtensorMap &mv, const AttnPrefillKArgs &k, uint32_t grid, cudaStream_t stream, bool pdl) {
     constexpr size_t smemBytes = (size_t)(HD / 64) * kApAtomBytes * 5 + 2 * kApAtomBytes + 256 + 1024;
     static bool configured = false;
     if (!configured) {
         DL_CUDA_CHECK(cudaFuncSetAttribute(attnPrefillTcKernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
         configured = true;
     }
-    attnPrefillTcKernel<HD><<<grid, kApThreads, smemBytes, stream>>>(mk, mv, k);
+    DL_CUDA_CHECK(launchPdl(attnPrefillTcKernel<HD>, dim3(grid), dim3(kApThreads), smemBytes, stream, pdl, mk, mv, k));
     DL_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -379,7 +381,7 @@ int apLaunch(const CUtensorMap &mk, const CUtensorMap &mv, const AttnPrefillKArg
 }  // namespace
 
 // Returns 1 when the shape is not covered (caller falls back to the per-token kernel).
-int launchAttnPrefillTc(const AttnPrefillArgs &a, cudaStream_t stream) {
+int launchAttnPrefillTc(const AttnPrefillArgs &a, cudaStream_t stream, bool pdl) {
     if (a.headDim != 64 && a.headDim != 128) return 1;
     if (a.nKvHeads == 0 || a.nHeads % a.nKvHeads) return 1;
     const uint32_t kvMul = a.nHeads / a.nKvHeads;
@@ -394,7 +396,7 @@ int launchAttnPrefillTc(const AttnPrefillArgs &a, cudaStream_t stream) {
     const uint64_t rows = (uint64_t)a.nKvHeads * a.seqLen;
     if (!apCacheMap(&mk, a.kCache, a.headDim, rows) || !apCacheMap(&mv, a.vCache, a.headDim, rows)) return -2;
     const uint32_t grid = a.nKvHeads * k.nQTiles;
-    return a.headDim == 128 ? apLaunch<128>(mk, mv, k, grid, stream) : apLaunch<64>(mk, mv, k, grid, stream);
+    return a.headDim == 128 ? apLaunch<128>(mk, mv, k, grid, stream, pdl) : apLaunch<64>(mk, mv, k, grid, stream, pdl);
 }
 
 }  // namespace dl

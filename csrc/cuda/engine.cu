@@ -261,7 +261,7 @@ static int engineForward(Engine &e, int nb, int logitsMode, bool greedyAdvance, 
 static int enginePrefill(Engine &e, uint32_t T, uint32_t p0, int wantLogits, cudaStream_t stream) {
     const EngineConfig &c = e.cfg;
     const GlobalPtrs &g = e.g;
-    const bool pdl = false;   // plain stream order between the heterogeneous kernels of this path
+    const bool pdl = c.usePdl != 0;   // every kernel of this chain waits (griddepcontrol.wait) before touching its predecessor's data
     const uint32_t qDim = c.nHeads * c.headDim, kvDim = c.nKvHeads * c.headDim, qkvDim = qDim + 2 * kvDim;
     if (T < 1 || T > g.maxPrefill || T > 256) return -11;
     if (c.wType != 0) return -35;   // tensor-core path: q40 matrices
@@ -277,7 +277,7 @@ static int enginePrefill(Engine &e, uint32_t T, uint32_t p0, int wantLogits, cud
     DL_TRY(launchEmbedding(embTable(e), g.pTokens, g.px, c.dim, c.dim, g.vocabFull, (int)T, stream));
     for (uint32_t l = 0; l < c.nLayers; l++) {
         const LayerPtrs &L = e.layers[l];
-        DL_TRY(launchRmsNormBf16(g.px, c.dim, L.norm0, g.pxn, c.dim, c.dim, c.eps, T, stream));
+        DL_TRY(launchRmsNormBf16(g.px, c.dim, L.norm0, g.pxn, c.dim, c.dim, c.eps, T, stream, pdl));
         DL_TRY(gemmQ40Tc(GEPI_STORE_F32_, L.qkvQs, L.qkvSc, qkvDim, c.dim, g.pxn, c.dim, T, g.pqkv, qkvDim, c.numSms, stream, pdl));
         RopeKvArgs r{};
         r.qkv = g.pqkv; r.qkvStride = qkvDim; r.pos = g.pPos; r.rope = g.rope; r.qNorm = L.qNorm; r.kNorm = L.kNorm;
@@ -291,7 +291,7 @@ static int enginePrefill(Engine &e, uint32_t T, uint32_t p0, int wantLogits, cud
             ap.qkv = g.pqkv; ap.qkvStride = qkvDim; ap.T = T; ap.p0 = p0; ap.nHeads = c.nHeads; ap.nKvHeads = c.nKvHeads;
             ap.headDim = c.headDim; ap.seqLen = c.seqLen; ap.kCache = r.kCache; ap.vCache = r.vCache;
             ap.out = (__nv_bfloat16 *)g.pzb; ap.outStride = qDim;
-            attnRc = launchAttnPrefillTc(ap, stream);
+            attnRc = launchAttnPrefillTc(ap, stream, pdl);
             if (attnRc < 0) return attnRc;
         }
         if (attnRc == 1) {
@@ -306,7 +306,7 @@ static int enginePrefill(Engine &e, uint32_t T, uint32_t p0, int wantLogits, cud
         if (tp && !e.prefillFusedAr) {
             arP.parity = 0;
             DL_TRY(gemmQ40Tc(GEPI_STORE_F32_, L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.pqkv, c.dim, c.numSms, stream, pdl));
-            DL_TRY(launchArResidual(g.px, g.pqkv, c.dim, T, arP, stream));
+            DL_TRY(launchArResidual(g.px, g.pqkv, c.dim, T, arP, stream, pdl));
         } else if (tp) { arP.parity = 0; DL_TRY(gemmQ40TcAr(L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, arP)); }
         else DL_TRY(gemmQ40Tc(GEPI_RESIDUAL_, L.woQs, L.woSc, c.dim, qDim, g.pzb, qDim, T, g.px, c.dim, c.numSms, stream, pdl));
         if (c.nExperts > 0) {
@@ -320,12 +320,12 @@ static int enginePrefill(Engine &e, uint32_t T, uint32_t p0, int wantLogits, cud
             if (mr != 0) return mr == 1 ? -36 : mr;
             continue;
         }
-        DL_TRY(launchRmsNormBf16(g.px, c.dim, L.norm1, g.pxn, c.dim, c.dim, c.eps, T, stream));
+        DL_TRY(launchRmsNormBf16(g.px, c.dim, L.norm1, g.pxn, c.dim, c.dim, c.eps, T, stream, pdl));
         DL_TRY(gemmQ40Tc(GEPI_SWIGLU_BF16_, L.w13Qs, L.w13Sc, 2 * c.ffDim, c.dim, g.pxn, c.dim, T, g.phb, c.ffDim, c.numSms, stream, pdl));
         if (tp && !e.prefillFusedAr) {
             arP.parity = 1;
             DL_TRY(gemmQ40Tc(GEPI_STORE_F32_, L.w2Qs, L.w2Sc, c.dim, c.ffDim, g.phb, c.ffDim, T, g.pqkv, c.dim, c.numSms, stream, pdl));
-            DL_TRY(launchArResidual(g.px, g.pqkv, c.dim, T, arP, stream));
+            DL_TRY(launchArResidual(g.px, g.pqkv, c.dim, T, arP, stream, pdl));
         } else if (tp) { arP.parity = 1; DL_TRY(gemmQ40TcAr(L.w2Qs, L.w2Sc, c.dim, c.ffDim, g.phb, c.ffDim, T, g.px, c.dim, c.numSms, stream, arP)); }
         else DL_TRY(gemmQ40Tc(GEPI_RESIDUAL_, L.w2Qs, L.w2Sc, c.dim, c.ffDim, g.phb, c.ffDim, T, g.px, c.dim, c.numSms, stream, pdl));
     }

@@ -70,7 +70,7 @@ struct CommPtrs {   // mirrored by ctypes
     uint32_t nRanks, rank, maxCtas, slotStride;
     void *arena[kApiMaxRanks];          // every rank's symmetric arena mapped into this process
     void *mcArena;                      // NVLS multicast mapping of the arena (null: none)
-    uint64_t slotsOff, flagsOff, candValOff, candIdxOff, candFlagOff, gatherOff;
+    uint64_t slotsOff, flagsOff, candValOff, gatherOff;   // LL all-reduce slots, logits-gather arrival counters, arg-max candidates, gathered logits
     uint64_t prefillSlotsOff;        // LL slots for the prefill GEMM all-reduce: [2][nRanks][maxPrefill * dim]
     uint32_t prefillSlotStride;
 };

@@ -1013,9 +1013,8 @@ __global__ void __launch_bounds__(256) rmsNormBf16Kernel(const float *__restrict
 }
 
 int launchRmsNormBf16(const float *x, uint32_t xStride, const float *w, void *y, uint32_t yStride, uint32_t n, float eps, uint32_t T,
-                      cudaStream_t stream) {
-    rmsNormBf16Kernel<<<T, 256, 0, stream>>>(x, xStride, w, (__nv_bfloat16 *)y, yStride, n, eps);
-    DL_CUDA_CHECK(cudaGetLastError());
+                      cudaStream_t stream, bool pdl) {
+    DL_CUDA_CHECK(launchPdl(rmsNormBf16Kernel, dim3(T), dim3(256), 0, stream, pdl, x, xStride, w, (__nv_bfloat16 *)y, yStride, n, eps));
     return 0;
 }
 

@@ -100,7 +100,7 @@ struct AttnPrefillArgs {
     __nv_bfloat16 *out;          // [T][outStride], head h at columns h * headDim
     uint32_t outStride;
 };
-int launchAttnPrefillTc(const AttnPrefillArgs &a, cudaStream_t stream);   // 1: shape not covered
+int launchAttnPrefillTc(const AttnPrefillArgs &a, cudaStream_t stream, bool pdl = false);   // 1: shape not covered
 
 // Single-token decode attention with QK-norm + RoPE + KV-cache append fused in (no separate rope kernel).
 struct AttnFusedArgs {
@@ -225,8 +225,21 @@ struct MoePrefillArgs {
     ArArgs ar;                    // nRanks > 1: partial sums are all-reduced over peer memory inside the combine kernel
 };
 int moePrefillFfn(const MoePrefillArgs &a, cudaStream_t stream);   // 1: shape not covered
-int launchArResidual(float *x, const float *partial, uint32_t dim, uint32_t T, const ArArgs &ar, cudaStream_t stream);   // x += all-reduce(partial)
+// Launch with the programmatic-dependent-launch attribute: the kernel may start while its predecessor in the stream is still running
+// and must execute griddepcontrol.wait (pdlWait) before touching anything the predecessor produces or still reads.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+int launchArResidual(float *x, const float *partial, uint32_t dim, uint32_t T, const ArArgs &ar, cudaStream_t stream, bool pdl = false);   // x += all-reduce(partial)
 int launchRmsNormBf16(const float *x, uint32_t xStride, const float *w, void *y, uint32_t yStride, uint32_t n, float eps, uint32_t T,
-                      cudaStream_t stream);
+                      cudaStream_t stream, bool pdl = false);
 
 }  // namespace dl

@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(256) moeCombineKernel(float *x, uint32_t dim, 
 // polls). Push: one multimem.st per cell through the NVSwitch multicast mapping (or nRanks unicast stores); pull: the N source
 // slots of the cell, summed in rank order.
 __global__ void __launch_bounds__(256) arResidualKernel(float *x, const float *__restrict__ partial, uint32_t dim, uint32_t T, ArArgs ar) {
+    pdlLaunchDependents();
+    pdlWait();
     const uint32_t t = blockIdx.y;
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= dim || t >= T) return;
@@ -163,9 +165,8 @@ int moeEnsureScratch(uint32_t nPairs, uint32_t dim, uint32_t ff, uint32_t nExper
 
 }  // namespace
 
-int launchArResidual(float *x, const float *partial, uint32_t dim, uint32_t T, const ArArgs &ar, cudaStream_t stream) {
-    arResidualKernel<<<dim3((dim + 255) / 256, T), 256, 0, stream>>>(x, partial, dim, T, ar);
-    DL_CUDA_CHECK(cudaGetLastError());
+int launchArResidual(float *x, const float *partial, uint32_t dim, uint32_t T, const ArArgs &ar, cudaStream_t stream, bool pdl) {
+    DL_CUDA_CHECK(launchPdl(arResidualKernel, dim3((dim + 255) / 256, T), dim3(256), 0, stream, pdl, x, partial, dim, T, ar));
     return 0;
 }
 

@@ -8,7 +8,7 @@ Layout
   ops/       ctypes bindings of the hand-written sm_100a kernels (csrc/cuda)
   parallel/  one-process-per-GPU bootstrap, peer-memory arena, collectives
   runtime/   engine wrapper (CUDA-graph decode loop), generation drivers
-  text/      tokenizer, sampler, chat templates, stop detector    (native: csrc/host/text.cpp)
+  (tokenizer, sampler, chat templates, stop detector: native only, csrc/host/text.cpp, reached through host())
   apps/      `dllama` CLI and `dllama-api` HTTP server
 """
 __version__ = "0.1.0"

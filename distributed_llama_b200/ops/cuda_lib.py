@@ -38,7 +38,7 @@ class GlobalPtrs(C.Structure):
 
 class CommPtrs(C.Structure):
     _fields_ = [("nRanks", u32), ("rank", u32), ("maxCtas", u32), ("slotStride", u32), ("arena", vp * 8), ("mcArena", vp),
-                ("slotsOff", u64), ("flagsOff", u64), ("candValOff", u64), ("candIdxOff", u64), ("candFlagOff", u64),
+                ("slotsOff", u64), ("flagsOff", u64), ("candValOff", u64),
                 ("gatherOff", u64), ("prefillSlotsOff", u64), ("prefillSlotStride", u32)]
 
 

@@ -23,8 +23,6 @@ class ArenaLayout:
     slots_off: int
     flags_off: int
     cand_val_off: int
-    cand_idx_off: int
-    cand_flag_off: int
     gather_off: int
     prefill_slots_off: int
     prefill_slot_stride: int
@@ -36,13 +34,11 @@ def arena_layout(n_ranks: int, max_batch: int, dim: int, vocab_full: int, max_pr
         return (x + 255) // 256 * 256
     off = 0
     slots = off; off = align(off + 2 * n_ranks * max_batch * dim * 8)   # LL words: (f32 payload, flag)
-    flags = off; off = align(off + 2 * n_ranks * MAX_CTAS * 4)
+    flags = off; off = align(off + 2 * n_ranks * MAX_CTAS * 4)            # logits-gather arrival counters (sampler.cu)
     cv = off; off = align(off + 8 * 8)                                   # arg-max candidates, one LL word per rank
-    ci = off; off = align(off + 64)
-    cf = off; off = align(off + 64)
     gather = off; off = align(off + max_batch * vocab_full * 4)
     pslots = off; off = align(off + 2 * n_ranks * max_prefill * dim * 8)
-    return ArenaLayout(slots, flags, cv, ci, cf, gather, pslots, max_prefill * dim, off)
+    return ArenaLayout(slots, flags, cv, gather, pslots, max_prefill * dim, off)
 
 
 class Communicator:
@@ -167,8 +163,8 @@ class Communicator:
         arr = (C.c_void_p * 8)(*([C.c_void_p(p) for p in self.arena_ptrs] + [None] * (8 - len(self.arena_ptrs))))
         return cl.CommPtrs(nRanks=self.world_size, rank=self.rank, maxCtas=MAX_CTAS, slotStride=slot_stride, arena=arr,
                            mcArena=C.c_void_p(self.mc_ptr) if self.mc_ptr else None,
-                           slotsOff=L.slots_off, flagsOff=L.flags_off, candValOff=L.cand_val_off, candIdxOff=L.cand_idx_off,
-                           candFlagOff=L.cand_flag_off, gatherOff=L.gather_off, prefillSlotsOff=L.prefill_slots_off,
+                           slotsOff=L.slots_off, flagsOff=L.flags_off, candValOff=L.cand_val_off,
+                           gatherOff=L.gather_off, prefillSlotsOff=L.prefill_slots_off,
                            prefillSlotStride=L.prefill_slot_stride)
 
     # ---- baseline collectives (NCCL) ----

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 {
 if [ "$N" -le 2 ]; then MODELS="tiny-llama31 tiny-qwen3 tiny-qwen3-moe"; elif [ "$N" -le 4 ]; then MODELS="tiny-llama-tp8 tiny-llama-kvrep tiny-qwen3-moe"; else MODELS="tiny-llama-tp8 tiny-llama-kvrep"; fi
 for m in $MODELS; do
-  echo "== tp_check $m (multi-kernel decode)"; timeout 240 $TR tools/tp_check.py $m 2>&1 | grep -v "^W\|^\[W\|warn" | tail -4
+  if [ -z "$QUICK" ]; then echo "== tp_check $m (multi-kernel decode)"; timeout 240 $TR tools/tp_check.py $m 2>&1 | grep -v "^W\|^\[W\|warn" | tail -4; fi
   echo "== tp_check $m (persistent kernel)"; DL_MEGA=1 timeout 240 $TR tools/tp_check.py $m 2>&1 | grep -v "^W\|^\[W\|warn" | tail -4
 done
 echo "== bench.py --gpus $N"; timeout 400 $TR bench.py --gpus $N --steps 64 --warmup 4 2>&1 | grep "^{" | tail -1
