@@ -351,11 +351,12 @@ __device__ void megaGemv(const MegaArgs &m, const MegaSmem &sm, const MegaPhase 
                 SpinGuard g(m.abortFlag);
                 const bool timeIt = m.syncNs && blockIdx.x == 0 && tid == 0;     // "Sync" time of the CLI lines: wait for the peers' partial sums
                 const uint64_t tSync0 = timeIt ? globalTimerNs() : 0;
+                // (requesting the N words in batches of 4 before examining them measured 1092 vs 1145 tok/s at N = 8: kept sequential)
                 for (uint32_t sr = 0; sr < ar.nRanks; sr++) {
                     uint64_t *w = mine + (size_t)(arParity * ar.nRanks + sr) * ar.slotStride + rowBase + r;
                     uint2 v2 = ldLL(w);
                     while (v2.y == 0u && !g.tick()) v2 = ldLL(w);
-                    sum += __uint_as_float(v2.x);
+                    sum += __uint_as_float(v2.x);          // rank order: every rank computes the same sum
                     stLL(w, 0u, 0u);
                 }
                 if (timeIt) *m.syncNs += globalTimerNs() - tSync0;   // device-memory accumulator, touched by this one thread only

@@ -88,6 +88,7 @@ PRESETS: Dict[str, ModelConfig] = {
     "tiny-llama31": _llama3("tiny-llama31", 512, 1024, 3, 8, 4, seq=512, vocab=512),
     "tiny-llama-tp8": _llama3("tiny-llama-tp8", 1024, 2048, 2, 16, 8, seq=512, vocab=1024),
     "tiny-llama-kvrep": _llama3("tiny-llama-kvrep", 512, 1024, 2, 8, 2, seq=512, vocab=512),
+    "tiny-llama-kvrep8": _llama3("tiny-llama-kvrep8", 1024, 2048, 2, 16, 2, seq=512, vocab=1024),   # 8 ranks: 2 heads each, every KV head on 4 ranks
     "tiny-qwen3": ModelConfig("tiny-qwen3", ARCH_QWEN3, 256, 512, 2, 4, 2, 512, 256, head_dim=128,
                               rope_theta=1000000, norm_epsilon=6),
     "tiny-qwen3-moe": ModelConfig("tiny-qwen3-moe", ARCH_QWEN3_MOE, 256, 512, 2, 4, 2, 512, 256, head_dim=128,

@@ -128,9 +128,20 @@ def lib() -> C.CDLL:
     return L
 
 
+_ERRORS = {
+    -12: "prompt chunk larger than the prefill all-reduce slots of the peer arena",
+    -30: "tensor-parallel slice too narrow for the fused all-reduce GEMV: the per-rank K of WO / W2 (heads/N * headDim, ffDim/N) "
+         "must be a multiple of 128 — use fewer ranks, or DL_COLLECTIVES=nccl",
+    -31: "mixture-of-experts up-projection shape not covered by the TMA GEMV",
+    -32: "mixture-of-experts down-projection shape not covered by the TMA GEMV (per-rank expert ffDim must be a multiple of 128: use moe_mode=ep)",
+    -33: "arg-max under tensor parallelism needs the fused logits kernel",
+    -36: "mixture-of-experts prefill shape not covered (dim, ffDim multiples of 256, chunk <= 256 tokens)",
+}
+
+
 def check(code: int, what: str) -> None:
     if code != 0:
-        raise RuntimeError(f"{what} failed with code {code}")
+        raise RuntimeError(f"{what} failed with code {code}" + (f": {_ERRORS[code]}" if code in _ERRORS else ""))
 
 
 def stream_ptr() -> int:
