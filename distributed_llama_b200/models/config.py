@@ -5,7 +5,7 @@ Presets follow the published HF configs of the models in the reference's launch.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field, asdict
+from dataclasses import dataclass, replace, field, asdict
 from typing import Dict, Optional
 
 ARCH_LLAMA = 0xABCD00
@@ -73,6 +73,8 @@ PRESETS: Dict[str, ModelConfig] = {
     "llama-3.2-3b": _llama3("llama-3.2-3b", 3072, 8192, 28, 24, 8, scaling=32),
     "llama-3.1-8b": _llama3("llama-3.1-8b", 4096, 14336, 32, 32, 8),
     "llama-3.3-70b": _llama3("llama-3.3-70b", 8192, 28672, 80, 64, 8),
+    # the per-rank slice of Llama-3.1-8B at 8 ranks as a single-GPU model (tools/bench_config.py: kernel tuning for the N = 8 regime)
+    "llama-3.1-8b-slice8": replace(_llama3("llama-3.1-8b-slice8", 4096, 1792, 32, 4, 1, vocab=16032), head_dim=128),
     "llama-3.1-405b": _llama3("llama-3.1-405b", 16384, 53248, 126, 128, 8),
     "qwen3-0.6b": ModelConfig("qwen3-0.6b", ARCH_QWEN3, 1024, 3072, 28, 16, 8, 151936, 40960, head_dim=128,
                               rope_theta=1000000, norm_epsilon=6),
