@@ -1,7 +1,19 @@
 // `dllama-native {inference|perplexity|chat}` — the reference CLI (src/dllama.cpp:13-285, flag table src/app.cpp:24-135)
-// as one native binary on one B200: C++ tokenizer / sampler / chat templates (csrc/host), native engine driver
-// (native_engine.cpp), CUDA kernels from _cuda.so. No interpreter in the process. Tensor-parallel runs (root + workers, one
-// process per GPU) are started with `./dllama <mode> --gpus N`, which bootstraps the ranks through torch.distributed.
+// as one native binary: C++ tokenizer / sampler / chat templates (csrc/host), native engine driver (native_engine.cpp), CUDA
+// kernels from _cuda.so. No interpreter in the process.
+//
+// `--gpus N` (tensor parallel over the GPUs of one NVSwitch box) is the reference's root + `dllama worker` processes
+// (src/dllama.cpp:260-285, src/app.cpp:306-365) without sockets: the root forks one worker process per extra GPU *before* CUDA is
+// initialised; every process loads its slice of the model, joins the peer-memory arena (CUDA VMM handles passed over unix sockets,
+// csrc/cuda/comm_vmm.cu) and the workers then mirror the root's engine calls, which reach them through a control block in an
+// anonymous shared mapping (the reference's LlmControlPacket, src/app.hpp:46-49). A worker that dies is noticed by the root
+// (waitpid) and the root's death by the workers (getppid): nobody waits forever. The all-reduces themselves run inside the
+// kernels over NVLink.
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -9,6 +21,9 @@
 #include <cstring>
 #include <ctime>
 #include <iostream>
+#include <memory>
+#include <new>
+#include <csignal>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -27,14 +42,15 @@ struct Args {
     float temperature = 0.8f, topp = 0.9f;
     uint64_t seed = (uint64_t)std::time(nullptr);
     int gpuIndex = 0;
+    uint32_t gpus = 1;
 };
 
 const char *kUsage =
     "Usage: dllama-native {inference|perplexity|chat} --model <path> --tokenizer <path>\n"
     "        [--prompt <text>] [--steps <n>] [--temperature <t>] [--topp <p>] [--seed <s>] [--max-seq-len <n>]\n"
     "        [--chat-template {llama2|llama3|deepSeek3|chatml}] [--buffer-float-type q80] [--gpu-index <i>]\n"
-    "        (accepted for drop-in compatibility and ignored: --nthreads --net-turbo --gpu-segments --workers --host --port)\n"
-    "Tensor parallel over several GPUs: ./dllama <mode> ... --gpus N\n";
+    "        [--gpus <n>]   tensor parallel over GPUs gpu-index .. gpu-index + n - 1 of this machine (one process per GPU)\n"
+    "        (accepted for drop-in compatibility and ignored: --nthreads --net-turbo --gpu-segments --workers --host --port)\n";
 
 Args parse(int argc, char **argv) {
     Args a;
@@ -61,6 +77,7 @@ Args parse(int argc, char **argv) {
         else if (name == "--chat-template") a.chatTemplate = value;
         else if (name == "--buffer-float-type") a.bufferFloatType = value;
         else if (name == "--gpu-index") a.gpuIndex = std::max(0, std::stoi(value));
+        else if (name == "--gpus") a.gpus = (uint32_t)std::max(1, std::stoi(value));
         else if (name == "--nthreads" || name == "--net-turbo" || name == "--gpu-segments" || name == "--host" || name == "--port") {}
         else throw std::runtime_error("Unknown option: " + name);
         i += 2;
@@ -73,25 +90,140 @@ double nowMs() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+// ---- control block of a `--gpus N` job (anonymous shared mapping created before the fork) ----
+enum : uint32_t { OP_PREFILL = 1, OP_STEP_GREEDY = 2, OP_STEP_SAMPLED = 3, OP_EXIT = 4 };
+constexpr uint32_t kMaxRanks = 8, kCtrlTokens = 256;
+struct Control {
+    std::atomic<uint32_t> seq;              // bumped by the root for every command
+    std::atomic<uint32_t> ack[kMaxRanks];   // last command completed by rank r
+    std::atomic<uint32_t> arrived;          // bootstrap barrier: monotonic arrival counter
+    std::atomic<int32_t> failedRank;        // rank + 1 of the first process that failed, 0 = none
+    uint32_t op, n, pos;
+    float temperature, topp;
+    int32_t tokens[kCtrlTokens];
+    char error[240];
+};
+
+struct Job {   // this process's view of the job
+    Control *ctl = nullptr;
+    uint32_t rank = 0, nRanks = 1, barriers = 0;
+    pid_t rootPid = 0;
+    std::string tag;
+
+    void fail(const std::string &what) {
+        if (!ctl) return;
+        int32_t none = 0;
+        if (ctl->failedRank.compare_exchange_strong(none, (int32_t)rank + 1)) std::snprintf(ctl->error, sizeof(ctl->error), "%s", what.c_str());
+    }
+    void checkPeers() {
+        if (ctl->failedRank.load() != 0 && ctl->failedRank.load() != (int32_t)rank + 1)
+            throw std::runtime_error("rank " + std::to_string(ctl->failedRank.load() - 1) + " failed: " + std::string(ctl->error));
+        if (rank == 0) {
+            int st = 0;
+            const pid_t p = waitpid(-1, &st, WNOHANG);
+            if (p > 0) throw std::runtime_error("a worker process exited unexpectedly");
+        } else if (getppid() != rootPid) {
+            throw std::runtime_error("the root process is gone");
+        }
+    }
+    // spins while the job is active, sleeps between probes after 1 s of waiting (the reference's "turbo off")
+    template <typename Pred> void waitFor(Pred done) {
+        const double t0 = nowMsJob();
+        for (uint32_t i = 0; !done(); i++) {
+            if ((i & 1023u) == 1023u) {
+                checkPeers();
+                if (nowMsJob() - t0 > 1000.0) usleep(200);
+            }
+        }
+    }
+    static double nowMsJob() {
+        using namespace std::chrono;
+        return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+    }
+    void barrier() {   // all ranks, bootstrap only
+        barriers++;
+        ctl->arrived.fetch_add(1);
+        const uint32_t target = barriers * nRanks;
+        waitFor([&] { return ctl->arrived.load() >= target; });
+    }
+    // root: publish a command after every worker has finished the previous one
+    void issue(uint32_t op, const int32_t *tokens, uint32_t n, uint32_t pos, float temperature = 0.f, float topp = 0.f) {
+        if (nRanks == 1) return;
+        const uint32_t cur = ctl->seq.load();
+        waitFor([&] { for (uint32_t r = 1; r < nRanks; r++) if (ctl->ack[r].load() != cur) return false; return true; });
+        ctl->op = op; ctl->n = n; ctl->pos = pos; ctl->temperature = temperature; ctl->topp = topp;
+        for (uint32_t i = 0; i < n && i < kCtrlTokens; i++) ctl->tokens[i] = tokens[i];
+        ctl->seq.store(cur + 1, std::memory_order_release);
+    }
+};
+
 struct App {
     Args args;
+    Job &job;
     NativeEngine engine;
     Tokenizer tokenizer;
     Sampler sampler;
-    App(const Args &a)
-        : args(a), engine(a.model, a.maxSeqLen, a.gpuIndex), tokenizer(a.tokenizer),
+    App(const Args &a, Job &j)
+        : args(a), job(j), engine(a.model, a.maxSeqLen, a.gpuIndex + (int)j.rank, j.rank, j.nRanks, j.tag, [&j] { j.barrier(); }),
+          tokenizer(a.tokenizer),
           sampler(std::min<uint32_t>(tokenizer.vocabSize(), engine.header().vocabSize), a.temperature, a.topp, a.seed) {
         // sampling ranges over the tokenizer's vocabulary (reference src/app.cpp:243-246); padded embedding rows never win
         engine.setVocabLimit(tokenizer.vocabSize());
+        if (j.nRanks > 1) engine.seedSampler(a.seed);   // device sampler: every rank draws the same token from the same stream
+    }
+
+    void prefill(const std::vector<int32_t> &tokens, uint32_t pos) {
+        for (size_t i = 0; i < tokens.size(); i += 192) {   // one control packet per tensor-core chunk
+            const uint32_t n = (uint32_t)std::min<size_t>(192, tokens.size() - i);
+            job.issue(OP_PREFILL, tokens.data() + i, n, pos + (uint32_t)i);
+            engine.prefill(std::vector<int32_t>(tokens.begin() + i, tokens.begin() + i + n), pos + (uint32_t)i);
+        }
     }
 
     int32_t next(int32_t token, uint32_t pos) {
-        if (sampler.temperature() == 0.f) return engine.stepGreedy(token, pos);
+        if (sampler.temperature() == 0.f) {
+            job.issue(OP_STEP_GREEDY, &token, 1, pos);
+            return engine.stepGreedy(token, pos);
+        }
+        if (job.nRanks > 1) {   // logits stay sharded on the devices: temperature / top-p on the device
+            job.issue(OP_STEP_SAMPLED, &token, 1, pos, sampler.temperature(), args.topp);
+            return engine.stepSampled(token, pos, sampler.temperature(), args.topp);
+        }
         const float *logits = engine.step(token, pos);
         std::vector<float> tmp(logits, logits + std::min<uint32_t>(tokenizer.vocabSize(), engine.header().vocabSize));
         return sampler.sample(tmp.data());
     }
 };
+
+// ranks >= 1: mirror the root's engine calls until OP_EXIT (reference: runWorkerApp, src/app.cpp:306-365)
+int workerMain(const Args &a, Job &job) {
+    try {
+        NativeEngine engine(a.model, a.maxSeqLen, a.gpuIndex + (int)job.rank, job.rank, job.nRanks, job.tag, [&job] { job.barrier(); });
+        {
+            Tokenizer tok(a.tokenizer);      // only for the vocabulary limit of the greedy arg-max (must match the root)
+            engine.setVocabLimit(tok.vocabSize());
+        }
+        engine.seedSampler(a.seed);
+        job.barrier();                       // "weights loaded" on every rank
+        uint32_t mine = 0;
+        while (true) {
+            job.waitFor([&] { return job.ctl->seq.load(std::memory_order_acquire) != mine; });
+            mine++;
+            const Control &c = *job.ctl;
+            if (c.op == OP_EXIT) break;
+            if (c.op == OP_PREFILL) engine.prefill(std::vector<int32_t>(c.tokens, c.tokens + c.n), c.pos);
+            else if (c.op == OP_STEP_GREEDY) engine.stepGreedy(c.tokens[0], c.pos);
+            else if (c.op == OP_STEP_SAMPLED) engine.stepSampled(c.tokens[0], c.pos, c.temperature, c.topp);
+            if (c.op == OP_PREFILL) engine.synchronize();
+            job.ctl->ack[job.rank].store(mine, std::memory_order_release);
+        }
+        job.ctl->ack[job.rank].store(mine, std::memory_order_release);
+        return 0;
+    } catch (const std::exception &e) {
+        job.fail(e.what());
+        return 1;
+    }
+}
 
 void inference(App &app) {
     const Args &a = app.args;
@@ -109,7 +241,7 @@ void inference(App &app) {
     while (pos + 1 < nIn) {
         const uint32_t n = std::min(chunk, nIn - 1 - pos);
         const double t0 = nowMs();
-        app.engine.prefill(std::vector<int32_t>(tokens.begin() + pos, tokens.begin() + pos + n), pos);
+        app.prefill(std::vector<int32_t>(tokens.begin() + pos, tokens.begin() + pos + n), pos);
         app.engine.synchronize();
         const double dt = nowMs() - t0;
         evalMs += dt;
@@ -141,6 +273,7 @@ void inference(App &app) {
 
 void perplexity(App &app) {
     const Args &a = app.args;
+    if (app.job.nRanks > 1) throw std::runtime_error("perplexity needs the full logits on the host: run it on one GPU (or through ./dllama perplexity --gpus N)");
     if (!a.hasPrompt) throw std::runtime_error("Prompt is required");
     const ModelHeader &h = app.engine.header();
     const std::vector<int32_t> tokens = app.tokenizer.encode(a.prompt, true, true);
@@ -194,7 +327,7 @@ void chat(App &app) {
         const std::vector<int32_t> tokens = app.tokenizer.encode(g.content, pos == 0, true);
         const uint32_t end = std::min<uint32_t>(h.seqLen, pos + (uint32_t)tokens.size() - 1);
         const uint32_t n = end - pos;
-        app.engine.prefill(std::vector<int32_t>(tokens.begin(), tokens.begin() + n), pos);
+        app.prefill(std::vector<int32_t>(tokens.begin(), tokens.begin() + n), pos);
         pos += n;
         int32_t token = n < tokens.size() ? tokens[n] : tokens.back();
         app.tokenizer.resetDecoder();
@@ -225,20 +358,73 @@ int main(int argc, char **argv) {
         const Args a = parse(argc, argv);
         if (a.help || a.mode.empty()) { std::printf("%s", kUsage); return 0; }
         if (a.mode == "worker")
-            throw std::runtime_error("workers are ranks of a `./dllama <mode> --gpus N` (torch.distributed) job; dllama-native drives one GPU");
+            throw std::runtime_error("workers are forked by the root: dllama-native <mode> --gpus N");
         if (a.mode != "inference" && a.mode != "perplexity" && a.mode != "chat") throw std::runtime_error("Unsupported mode");
         if (a.model.empty()) throw std::runtime_error("Model is required");
         if (a.tokenizer.empty()) throw std::runtime_error("Tokenizer is required");
         if (a.bufferFloatType != "q80") throw std::runtime_error("This version supports only Q40 weights with Q80 sync type");
-        App app(a);
+        // ---- tensor-parallel job: fork the workers before CUDA exists in this process ----
+        Job job;
+        job.nRanks = std::min(a.gpus, kMaxRanks);
+        job.rootPid = getpid();
+        std::vector<pid_t> children;
+        if (job.nRanks > 1) {
+            void *p = mmap(nullptr, sizeof(Control), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+            if (p == MAP_FAILED) throw std::runtime_error("cannot map the control block");
+            job.ctl = new (p) Control();
+            job.tag = "dllama-" + std::to_string((long)getpid()) + "-" + std::to_string((long long)std::time(nullptr));
+            std::fflush(stdout);
+            for (uint32_t r = 1; r < job.nRanks; r++) {
+                const pid_t pid = fork();
+                if (pid < 0) throw std::runtime_error("fork failed");
+                if (pid == 0) {
+                    job.rank = r;
+                    std::fclose(stdin);
+                    const int rc = workerMain(a, job);
+                    std::fflush(stdout);
+                    _exit(rc);
+                }
+                children.push_back(pid);
+            }
+        }
+        struct Reaper {   // root: tell the workers to leave and collect them, whatever happens
+            Job &job; std::vector<pid_t> &children;
+            ~Reaper() {
+                if (job.nRanks <= 1 || job.rank != 0) return;
+                const uint32_t cur = job.ctl->seq.load();
+                job.ctl->op = OP_EXIT;
+                job.ctl->seq.store(cur + 1, std::memory_order_release);
+                for (pid_t c : children) {
+                    for (int i = 0; i < 3000; i++) {   // 3 s grace, then SIGKILL
+                        int st = 0;
+                        if (waitpid(c, &st, WNOHANG) != 0) { c = 0; break; }
+                        usleep(1000);
+                    }
+                    if (c) { kill(c, SIGKILL); waitpid(c, nullptr, 0); }
+                }
+            }
+        } reaper{job, children};
+        std::unique_ptr<App> appPtr;
+        try {
+            appPtr.reset(new App(a, job));
+            if (job.nRanks > 1) job.barrier();   // every rank has its weights
+        } catch (const std::exception &e) {
+            job.fail(e.what());
+            throw;
+        }
+        App &app = *appPtr;
         const ModelHeader &h = app.engine.header();
         if (app.tokenizer.vocabSize() != h.vocabSize)
             std::printf("Tokenizer vocab size (%u) does not match the model vocab size (%u)\n", app.tokenizer.vocabSize(), h.vocabSize);
         std::printf("%s", app.tokenizer.describe().c_str());
         std::printf("%s", describeModelHeader(h).c_str());
         std::printf("📀 RequiredMemory: %llu MB\n", (unsigned long long)(requiredDeviceBytes(h, 1, 2) / (1024 * 1024)));
-        std::printf("🧠 GPU %d: sm_100a kernels, %s decode; %.2f GB of weights uploaded\n", a.gpuIndex,
-                    app.engine.persistentKernel() ? "persistent-kernel" : "multi-kernel", app.engine.bytesUploaded() / 1e9);
+        if (job.nRanks > 1)
+            std::printf("🔗 %u GPUs (one process each), all-reduce inside the kernels over %s\n", job.nRanks,
+                        app.engine.multicast() ? "the NVSwitch multicast mapping (multimem.st)" : "NVLink peer memory");
+        std::printf("🧠 GPU %d: sm_100a kernels, %s decode; %.2f GB of weights uploaded%s\n", a.gpuIndex,
+                    app.engine.persistentKernel() ? "persistent-kernel" : "multi-kernel", app.engine.bytesUploaded() / 1e9,
+                    job.nRanks > 1 ? " by this rank" : "");
         std::printf("💿 Weights loaded\n");
         if (a.mode == "inference") inference(app);
         else if (a.mode == "perplexity") perplexity(app);

@@ -51,6 +51,7 @@ struct Q40Dev {   // device layout of csrc/cuda/common.cuh: qs u32 [rows][n/8], 
 struct NativeEngine::Impl {
     std::vector<void *> allocations;
     void *engine = nullptr;
+    void *vmm = nullptr;               // peer-memory arena handle (tensor parallel)
     cudaStream_t stream = nullptr;
     // weights
     float *embedding = nullptr, *finalNorm = nullptr, *rope = nullptr;
@@ -82,7 +83,9 @@ void *NativeEngine::dev(size_t bytes) {
     return p;
 }
 
-NativeEngine::NativeEngine(const std::string &modelPath, uint32_t maxSeqLen, int device) {
+NativeEngine::NativeEngine(const std::string &modelPath, uint32_t maxSeqLen, int device, uint32_t rank, uint32_t nRanks,
+                           const std::string &commTag, std::function<void()> hostBarrier) {
+    rank_ = rank; nRanks_ = std::max(1u, nRanks);
     h_ = loadModelHeader(modelPath, maxSeqLen);
     if (h_.weightType != F_Q40)
         throw std::runtime_error("dllama-native runs q40 weight files; f32/f16/q80 files are served by the Python front end (./dllama)");
@@ -96,12 +99,28 @@ NativeEngine::NativeEngine(const std::string &modelPath, uint32_t maxSeqLen, int
         for (const TensorEntry &t : dir_) impl_->index[std::make_tuple(t.name, t.layer, t.expert)] = &t;
         int sms = 0;
         cudaCheck(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");
-        const uint32_t hd = h_.headDim, dim = h_.dim, ff = h_.ffDim(), vocab = h_.vocabSize;
-        const uint32_t qDim = h_.nHeads * hd, kvDim = h_.nKvHeads * hd;
+        const uint32_t hd = h_.headDim, dim = h_.dim, vocab = h_.vocabSize, N = nRanks_;
+        // tensor-parallel placement (same rules as distributed_llama_b200/models/loader.py; reference slicers src/nn/nn-core.cpp:223-322):
+        // more ranks than KV heads -> nRanks / nKvHeads ranks share one KV head, each with its own query heads of that group
+        uint32_t kvRep = 1;
+        if (N > h_.nKvHeads) {
+            if (N % h_.nKvHeads || (h_.nHeads / h_.nKvHeads) % (N / h_.nKvHeads))
+                throw std::runtime_error("the number of GPUs must be a multiple of nKvHeads that divides the query heads of a KV group");
+            kvRep = N / h_.nKvHeads;
+        }
+        if (h_.nHeads % N || (kvRep == 1 && h_.nKvHeads % N) || h_.ffDim() % N || vocab % N)
+            throw std::runtime_error("nHeads, nKvHeads, ffDim and vocabSize must be divisible by the number of GPUs");
+        headsL_ = h_.nHeads / N; kvHeadsL_ = kvRep > 1 ? 1 : h_.nKvHeads / N;
+        kvRank_ = rank_ / kvRep; kvSlices_ = N / kvRep;
+        ffL_ = h_.ffDim() / N; vocabL_ = vocab / N;
+        const uint32_t ff = ffL_;
+        const uint32_t qDim = headsL_ * hd, kvDim = kvHeadsL_ * hd;
+        if (N > 1 && (qDim % 128 || ff % 128))
+            throw std::runtime_error("per-GPU slices of WO / W2 must be multiples of 128 columns (use fewer GPUs)");
         qkvDim_ = qDim + 2 * kvDim;
         const bool moe = h_.nExperts > 0;
         maxBatch_ = moe ? 1 : 8;
-        nSplits_ = (uint32_t)std::max(1, std::min(32, (2 * sms) / (int)std::max(1u, h_.nHeads)));
+        nSplits_ = (uint32_t)std::max(1, std::min(32, (2 * sms) / (int)std::max(1u, headsL_)));
 
         Mapping file(modelPath);
         uploadWeights(file.data);
@@ -112,29 +131,29 @@ NativeEngine::NativeEngine(const std::string &modelPath, uint32_t maxSeqLen, int
         I.tokens = (int32_t *)dev(mb * 4); I.pos = (int32_t *)dev(mb * 4);
         float *x = (float *)dev((size_t)mb * dim * 4), *qkv = (float *)dev((size_t)mb * qkvDim_ * 4), *z = (float *)dev((size_t)mb * qDim * 4);
         float *hbuf = (float *)dev((size_t)std::max(mb, kAct) * ff * 4);
-        I.logits = (float *)dev((size_t)mb * vocab * 4);
+        I.logits = (float *)dev((size_t)mb * vocabL_ * 4);
         I.hostLogits.resize(vocab);
         I.history = (int32_t *)dev((size_t)(seqLen_ + 1) * 4);
         I.pTokens = (int32_t *)dev(mp * 4); I.pPos = (int32_t *)dev(mp * 4);
         GlobalPtrs g{};
         g.embedding = I.embedding; g.finalNorm = I.finalNorm; g.wclsQs = I.wcls.qs; g.wclsSc = I.wcls.scales; g.rope = I.rope;
         g.vocabFull = vocab; g.tokens = I.tokens; g.pos = I.pos; g.x = x; g.qkv = qkv; g.z = z; g.h = hbuf; g.logits = I.logits;
-        g.attnPartial = (float *)dev((size_t)mb * h_.nHeads * nSplits_ * (hd + 2) * 4);
-        g.attnCounters = (unsigned int *)dev((size_t)mb * h_.nHeads * 4);
+        g.attnPartial = (float *)dev((size_t)mb * headsL_ * nSplits_ * (hd + 2) * 4);
+        g.attnCounters = (unsigned int *)dev((size_t)mb * headsL_ * 4);
         g.history = I.history;
         g.expertIdx = (int *)dev((size_t)mb * kAct * 4); g.expertWeight = (float *)dev((size_t)mb * kAct * 4);
         g.routerLogits = (float *)dev((size_t)mb * std::max(1u, h_.nExperts) * 4); g.routerCounter = (unsigned int *)dev(mb * 4);
         g.moeScratch = (float *)dev((size_t)kAct * dim * 4); g.moeCounters = (unsigned int *)dev(256 * 4);
         g.maxPrefill = mp; g.pTokens = I.pTokens; g.pPos = I.pPos;
-        g.px = (float *)dev((size_t)mp * dim * 4); g.pqkv = (float *)dev((size_t)mp * qkvDim_ * 4);
+        g.px = (float *)dev((size_t)mp * dim * 4); g.pqkv = (float *)dev((size_t)mp * std::max(qkvDim_, dim) * 4);   // also the [T][dim] partial product of the tensor-parallel WO / W2 GEMMs
         g.pxn = dev((size_t)mp * dim * 2); g.pzb = dev((size_t)mp * qDim * 2); g.phb = dev((size_t)mp * ff * 2);
-        g.pAttnPartial = (float *)dev((size_t)mp * h_.nHeads * (hd + 2) * 4); g.pAttnCounters = (unsigned int *)dev((size_t)mp * h_.nHeads * 4);
+        g.pAttnPartial = (float *)dev((size_t)mp * headsL_ * (hd + 2) * 4); g.pAttnCounters = (unsigned int *)dev((size_t)mp * headsL_ * 4);
         g.argVal = (float *)dev(256 * 4); g.argIdx = (int *)dev(256 * 4); g.argCounter = (unsigned int *)dev(16);
 
         EngineConfig cfg{};
-        cfg.dim = dim; cfg.nLayers = h_.nLayers; cfg.nHeads = h_.nHeads; cfg.nKvHeads = h_.nKvHeads; cfg.headDim = hd; cfg.ffDim = ff;
-        cfg.vocab = vocab; cfg.seqLen = seqLen_; cfg.nExperts = h_.nExperts; cfg.nActiveExperts = h_.nActiveExperts; cfg.maxBatch = mb;
-        cfg.nSplits = nSplits_; cfg.rank = 0; cfg.nRanks = 1; cfg.numSms = (uint32_t)sms; cfg.eps = h_.normEpsilon; cfg.usePdl = 1;
+        cfg.dim = dim; cfg.nLayers = h_.nLayers; cfg.nHeads = headsL_; cfg.nKvHeads = kvHeadsL_; cfg.headDim = hd; cfg.ffDim = ff;
+        cfg.vocab = vocabL_; cfg.seqLen = seqLen_; cfg.nExperts = h_.nExperts; cfg.nActiveExperts = h_.nActiveExperts; cfg.maxBatch = mb;
+        cfg.nSplits = nSplits_; cfg.rank = rank_; cfg.nRanks = N; cfg.numSms = (uint32_t)sms; cfg.eps = h_.normEpsilon; cfg.usePdl = 1;
         cfg.moeFirstExpert = 0; cfg.moeNumLocal = h_.nExperts; cfg.wType = 0;
         cfg.hiddenAct = h_.hiddenAct == ACT_GELU ? 1u : 0u;
         I.engine = dl_engine_create(&cfg);
@@ -149,6 +168,31 @@ NativeEngine::NativeEngine(const std::string &modelPath, uint32_t maxSeqLen, int
             engCheck(dl_engine_set_layer(I.engine, l, &lp), "dl_engine_set_layer");
         }
         engCheck(dl_engine_set_globals(I.engine, &g), "dl_engine_set_globals");
+        if (N > 1) {
+            // symmetric peer-memory arena, same layout as distributed_llama_b200/parallel/comm.py:arena_layout
+            auto align = [](uint64_t x) { return (x + 255) / 256 * 256; };
+            const uint32_t maxCtas = 256;
+            CommPtrs cp{};
+            uint64_t off = 0;
+            cp.slotsOff = off; off = align(off + 2ull * N * mb * dim * 8);            // LL words of the decode all-reduce
+            cp.flagsOff = off; off = align(off + 2ull * N * maxCtas * 4);             // logits-gather arrival counters
+            cp.candValOff = off; off = align(off + 8 * 8);                            // cross-rank arg-max candidates
+            cp.gatherOff = off; off = align(off + (uint64_t)mb * vocab * 4);          // gathered logits (device sampler)
+            cp.prefillSlotsOff = off; off = align(off + 2ull * N * mp * dim * 8);     // LL words of the prefill all-reduce
+            I.vmm = dl_vmm_create(rank_, N, off, commTag.c_str(), 1);
+            if (!I.vmm) throw std::runtime_error("cannot create the peer-memory arena (CUDA VMM with POSIX file-descriptor handles is required)");
+            if (hostBarrier) hostBarrier();      // every rank has bound its bootstrap socket
+            engCheck(dl_vmm_connect(I.vmm), "dl_vmm_connect");
+            cudaCheck(cudaMemsetAsync(dl_vmm_ptr(I.vmm, rank_), 0, off, I.stream), "cudaMemset(arena)");
+            cudaCheck(cudaStreamSynchronize(I.stream), "cudaMemset(arena)");
+            engCheck(dl_vmm_barrier(I.vmm, 3), "dl_vmm_barrier");   // nobody pushes into an arena that is still being cleared
+            cp.nRanks = N; cp.rank = rank_; cp.maxCtas = maxCtas; cp.slotStride = mb * dim;
+            for (uint32_t r = 0; r < N; r++) cp.arena[r] = dl_vmm_ptr(I.vmm, r);
+            cp.mcArena = dl_vmm_mc_ptr(I.vmm);
+            multicast_ = cp.mcArena != nullptr;
+            cp.prefillSlotStride = mp * dim;
+            engCheck(dl_engine_set_comm(I.engine, &cp), "dl_engine_set_comm");
+        }
         if (!moe) {
             engCheck(dl_engine_enable_mega(I.engine, 1), "dl_engine_enable_mega");   // falls back per call if the shape is unsupported
             mega_ = true;
@@ -164,6 +208,7 @@ void NativeEngine::release() {
     if (!impl_) return;
     cudaDeviceSynchronize();
     if (impl_->engine) dl_engine_destroy(impl_->engine);
+    if (impl_->vmm) dl_vmm_destroy(impl_->vmm);
     for (void *p : impl_->allocations) cudaFree(p);
     if (impl_->stream) cudaStreamDestroy(impl_->stream);
     delete impl_;
@@ -176,8 +221,8 @@ NativeEngine::~NativeEngine() { release(); }
 // NeoX (Qwen3) rotary layout re-ordered to adjacent pairs by the repack kernel, q_norm/k_norm permuted alike.
 void NativeEngine::uploadWeights(const uint8_t *file) {
     Impl &I = *impl_;
-    const uint32_t hd = h_.headDim, dim = h_.dim, ff = h_.ffDim(), vocab = h_.vocabSize;
-    const uint32_t qDim = h_.nHeads * hd, kvDim = h_.nKvHeads * hd;
+    const uint32_t hd = h_.headDim, dim = h_.dim, ff = ffL_, vocab = vocabL_;
+    const uint32_t qDim = headsL_ * hd, kvDim = kvHeadsL_ * hd;
     const bool neox = h_.ropeType == ROPE_FALCON;
     const uint32_t nExp = std::max(1u, h_.nExperts);
     cudaStream_t st = I.stream;
@@ -192,12 +237,30 @@ void NativeEngine::uploadWeights(const uint8_t *file) {
         w.scales = dev(rows * (n / 32) * 2);
         return w;
     };
-    auto repackRows = [&](const TensorEntry &t, const Q40Dev &dst, uint32_t dstStride, uint32_t dstOff, uint32_t headDim) {
-        cudaCheck(cudaMemcpyAsync(staging, file + t.offset, t.nBytes, cudaMemcpyHostToDevice, st), "cudaMemcpy(weights)");
-        engCheck(dl_repack_q40(staging, (t.n / 32) * 18, 0, (uint32_t)t.d, (uint32_t)(t.n / 32), dst.qs, dst.scales, dstStride, dstOff, headDim, st),
-                 "dl_repack_q40");
+    // rows [slice * rowsLocal, (slice + 1) * rowsLocal) of a file tensor: one contiguous byte range (the reference's row split)
+    auto repackRows = [&](const TensorEntry &t, const Q40Dev &dst, uint32_t dstStride, uint32_t dstOff, uint32_t headDim, uint32_t rowsLocal,
+                          uint32_t slice) {
+        const uint64_t rowBytes = (t.n / 32) * 18, bytes = rowBytes * rowsLocal;
+        cudaCheck(cudaMemcpyAsync(staging, file + t.offset + (uint64_t)slice * bytes, bytes, cudaMemcpyHostToDevice, st), "cudaMemcpy(weights)");
+        engCheck(dl_repack_q40(staging, rowBytes, 0, rowsLocal, (uint32_t)(t.n / 32), dst.qs, dst.scales, dstStride, dstOff, headDim, st), "dl_repack_q40");
         cudaCheck(cudaStreamSynchronize(st), "repack");   // the staging buffer is re-used by the next tensor
-        bytesUploaded_ += t.nBytes;
+        bytesUploaded_ += bytes;
+    };
+    // columns [slice * colsLocal, (slice + 1) * colsLocal) of every row (the reference's column split, src/nn/nn-core.cpp:307-322):
+    // the rank's 18-byte blocks are gathered on the host so that only its bytes cross PCIe
+    std::vector<uint8_t> gather;
+    auto repackCols = [&](const TensorEntry &t, const Q40Dev &dst, uint32_t dstOff, uint32_t colsLocal, uint32_t slice) {
+        const uint64_t rowBytes = (t.n / 32) * 18, locBytes = (uint64_t)(colsLocal / 32) * 18;
+        const uint8_t *src = file + t.offset;
+        if (locBytes != rowBytes) {
+            gather.resize((size_t)t.d * locBytes);
+            for (uint64_t r = 0; r < t.d; r++) std::memcpy(gather.data() + r * locBytes, file + t.offset + r * rowBytes + (uint64_t)slice * locBytes, locBytes);
+            src = gather.data();
+        }
+        cudaCheck(cudaMemcpyAsync(staging, src, (size_t)t.d * locBytes, cudaMemcpyHostToDevice, st), "cudaMemcpy(weights)");
+        engCheck(dl_repack_q40(staging, locBytes, 0, (uint32_t)t.d, colsLocal / 32, dst.qs, dst.scales, 1, dstOff, 0, st), "dl_repack_q40");
+        cudaCheck(cudaStreamSynchronize(st), "repack");
+        bytesUploaded_ += (uint64_t)t.d * locBytes;
     };
     auto f32Tensor = [&](const TensorEntry &t, const std::vector<uint32_t> *perm = nullptr) {
         const size_t count = (size_t)t.d * t.n;
@@ -220,7 +283,7 @@ void NativeEngine::uploadWeights(const uint8_t *file) {
     I.embedding = f32Tensor(I.entry("embedding"));
     I.finalNorm = f32Tensor(I.entry("final_norm"));
     I.wcls = q40Alloc(vocab, dim);
-    repackRows(I.entry("final_matmul_logits"), I.wcls, 1, 0, 0);
+    repackRows(I.entry("final_matmul_logits"), I.wcls, 1, 0, 0, vocab, rank_);
     {
         std::vector<float> table((size_t)seqLen_ * hd);
         buildRopeTable(h_, seqLen_, table.data());
@@ -232,17 +295,17 @@ void NativeEngine::uploadWeights(const uint8_t *file) {
     for (uint32_t l = 0; l < h_.nLayers; l++) {
         Impl::Layer &L = I.layers[l];
         L.qkv = q40Alloc(qkvDim_, dim);
-        repackRows(I.entry("block_matmul_q", l), L.qkv, 1, 0, neox ? hd : 0);
-        repackRows(I.entry("block_matmul_k", l), L.qkv, 1, qDim, neox ? hd : 0);
-        repackRows(I.entry("block_matmul_v", l), L.qkv, 1, qDim + kvDim, 0);
+        repackRows(I.entry("block_matmul_q", l), L.qkv, 1, 0, neox ? hd : 0, qDim, rank_);
+        repackRows(I.entry("block_matmul_k", l), L.qkv, 1, qDim, neox ? hd : 0, kvDim, kvRank_);
+        repackRows(I.entry("block_matmul_v", l), L.qkv, 1, qDim + kvDim, 0, kvDim, kvRank_);
         L.wo = q40Alloc(dim, qDim);
-        repackRows(I.entry("block_matmul_wo", l), L.wo, 1, 0, 0);
+        repackCols(I.entry("block_matmul_wo", l), L.wo, 0, qDim, rank_);
         L.w13 = q40Alloc((uint64_t)nExp * 2 * ff, dim);
         L.w2 = q40Alloc((uint64_t)nExp * dim, ff);
         for (uint32_t e = 0; e < nExp; e++) {
-            repackRows(I.entry("block_matmul_w1", l, e), L.w13, 2, e * 2 * ff, 0);
-            repackRows(I.entry("block_matmul_w3", l, e), L.w13, 2, e * 2 * ff + 1, 0);
-            repackRows(I.entry("block_matmul_w2", l, e), L.w2, 1, e * dim, 0);
+            repackRows(I.entry("block_matmul_w1", l, e), L.w13, 2, e * 2 * ff, 0, ff, rank_);
+            repackRows(I.entry("block_matmul_w3", l, e), L.w13, 2, e * 2 * ff + 1, 0, ff, rank_);
+            repackCols(I.entry("block_matmul_w2", l, e), L.w2, e * dim, ff, rank_);
         }
         L.norm0 = f32Tensor(I.entry("block_norm_0", l));
         L.norm1 = f32Tensor(I.entry("block_norm_1", l));
@@ -251,8 +314,8 @@ void NativeEngine::uploadWeights(const uint8_t *file) {
             L.kNorm = f32Tensor(I.entry("block_norm_k", l), neox ? &perm : nullptr);
         }
         if (h_.nExperts > 0) L.moeGate = f32Tensor(I.entry("block_moe_gate", l));
-        L.kCache = dev((size_t)h_.nKvHeads * seqLen_ * hd * 2);
-        L.vCache = dev((size_t)h_.nKvHeads * seqLen_ * hd * 2);
+        L.kCache = dev((size_t)kvHeadsL_ * seqLen_ * hd * 2);
+        L.vCache = dev((size_t)kvHeadsL_ * seqLen_ * hd * 2);
     }
     cudaCheck(cudaStreamSynchronize(st), "weight upload");
     cudaFree(staging);
@@ -273,7 +336,7 @@ void NativeEngine::forward(uint32_t n, int logitsMode, bool greedyAdvance) {
 
 void NativeEngine::prefill(const std::vector<int32_t> &tokens, uint32_t pos) {
     if (pos + tokens.size() > seqLen_) throw std::runtime_error("position beyond the context length");
-    const bool tc = h_.nExperts == 0 || (h_.dim % 256 == 0 && h_.moeHiddenDim % 256 == 0);   // MoE: grouped tensor-core GEMMs need 256-wide K
+    const bool tc = h_.nExperts == 0 || (h_.dim % 256 == 0 && ffL_ % 256 == 0);   // MoE: grouped tensor-core GEMMs need 256-wide K
     size_t i = 0;
     while (i < tokens.size()) {
         const size_t rem = tokens.size() - i;
@@ -293,6 +356,7 @@ void NativeEngine::prefill(const std::vector<int32_t> &tokens, uint32_t pos) {
 }
 
 const float *NativeEngine::step(int32_t token, uint32_t pos) {
+    if (nRanks_ > 1) throw std::runtime_error("host-side logits are not gathered under tensor parallelism: use stepGreedy / stepSampled");
     if (pos >= seqLen_) throw std::runtime_error("position beyond the context length");
     setInputs(&token, 1, pos, false);
     forward(1, 1, false);
@@ -336,6 +400,22 @@ int32_t NativeEngine::stepGreedy(int32_t token, uint32_t pos) {
     int32_t next = 0;   // the arg-max kernel leaves the sampled token in tokens[0] (and advances pos[0]) on the device
     cudaCheck(cudaMemcpyAsync(&next, I.tokens, 4, cudaMemcpyDeviceToHost, I.stream), "cudaMemcpy(token)");
     cudaCheck(cudaStreamSynchronize(I.stream), "stepGreedy");
+    if (nRanks_ > 1 && dl_engine_aborted(I.engine)) throw std::runtime_error("device-side wait timed out: a tensor-parallel peer stopped responding");
+    return next;
+}
+
+void NativeEngine::seedSampler(uint64_t seed) { engCheck(dl_engine_sampler_seed(impl_->engine, seed), "dl_engine_sampler_seed"); }
+
+int32_t NativeEngine::stepSampled(int32_t token, uint32_t pos, float temperature, float topp) {
+    if (pos >= seqLen_) throw std::runtime_error("position beyond the context length");
+    Impl &I = *impl_;
+    setInputs(&token, 1, pos, false);
+    forward(1, 1, false);
+    engCheck(dl_engine_sample(I.engine, temperature, topp, I.stream), "dl_engine_sample");
+    int32_t next = 0;   // the sampler leaves the drawn token in tokens[0]
+    cudaCheck(cudaMemcpyAsync(&next, I.tokens, 4, cudaMemcpyDeviceToHost, I.stream), "cudaMemcpy(token)");
+    cudaCheck(cudaStreamSynchronize(I.stream), "stepSampled");
+    if (dl_engine_aborted(I.engine)) throw std::runtime_error("device-side wait timed out: a tensor-parallel peer stopped responding");
     return next;
 }
 

@@ -98,6 +98,14 @@ int dl_engine_forward_part(void *h, int nb, uint32_t layer, int part, float *ybu
 int dl_engine_prefill(void *h, uint32_t T, uint32_t p0, int wantLogits, cudaStream_t stream);   // T tokens staged in pTokens/pPos at positions p0 .. p0 + T - 1
 int dl_engine_capture_decode(void *h);
 int dl_engine_decode_graph(void *h, int nSteps, cudaStream_t stream);
+// symmetric peer-memory arena (csrc/cuda/comm_vmm.cu): create (local, binds the bootstrap socket) -> [job-wide barrier] -> connect
+// (collective: exchanges file descriptors, maps every peer, sets up the NVSwitch multicast mapping)
+void *dl_vmm_create(uint32_t rank, uint32_t nRanks, size_t bytes, const char *tag, int wantMulticast);
+int dl_vmm_connect(void *h);
+void *dl_vmm_ptr(void *h, uint32_t rank);
+void *dl_vmm_mc_ptr(void *h);
+int dl_vmm_barrier(void *h, uint32_t phase);   // host barrier over the bootstrap sockets, phase 3..14
+void dl_vmm_destroy(void *h);
 int dl_repack_q40(const void *src, uint64_t srcRowPitch, uint64_t srcColByteOffset, uint32_t rows, uint32_t blocksPerRow, void *dstQs,
                   void *dstScales, uint32_t dstRowStride, uint32_t dstRowOffset, uint32_t headDim, cudaStream_t stream);
 }
