@@ -10,6 +10,7 @@
 // (waitpid) and the root's death by the workers (getppid): nobody waits forever. The all-reduces themselves run inside the
 // kernels over NVLink.
 #include <sys/mman.h>
+#include <sys/prctl.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -30,6 +31,7 @@
 
 #include "../host/text.hpp"
 #include "native_engine.hpp"
+#include "tp_job.hpp"
 
 using namespace dl;
 
@@ -90,140 +92,31 @@ double nowMs() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-// ---- control block of a `--gpus N` job (anonymous shared mapping created before the fork) ----
-enum : uint32_t { OP_PREFILL = 1, OP_STEP_GREEDY = 2, OP_STEP_SAMPLED = 3, OP_EXIT = 4 };
-constexpr uint32_t kMaxRanks = 8, kCtrlTokens = 256;
-struct Control {
-    std::atomic<uint32_t> seq;              // bumped by the root for every command
-    std::atomic<uint32_t> ack[kMaxRanks];   // last command completed by rank r
-    std::atomic<uint32_t> arrived;          // bootstrap barrier: monotonic arrival counter
-    std::atomic<int32_t> failedRank;        // rank + 1 of the first process that failed, 0 = none
-    uint32_t op, n, pos;
-    float temperature, topp;
-    int32_t tokens[kCtrlTokens];
-    char error[240];
-};
-
-struct Job {   // this process's view of the job
-    Control *ctl = nullptr;
-    uint32_t rank = 0, nRanks = 1, barriers = 0;
-    pid_t rootPid = 0;
-    std::string tag;
-
-    void fail(const std::string &what) {
-        if (!ctl) return;
-        int32_t none = 0;
-        if (ctl->failedRank.compare_exchange_strong(none, (int32_t)rank + 1)) std::snprintf(ctl->error, sizeof(ctl->error), "%s", what.c_str());
-    }
-    void checkPeers() {
-        if (ctl->failedRank.load() != 0 && ctl->failedRank.load() != (int32_t)rank + 1)
-            throw std::runtime_error("rank " + std::to_string(ctl->failedRank.load() - 1) + " failed: " + std::string(ctl->error));
-        if (rank == 0) {
-            int st = 0;
-            const pid_t p = waitpid(-1, &st, WNOHANG);
-            if (p > 0) throw std::runtime_error("a worker process exited unexpectedly");
-        } else if (getppid() != rootPid) {
-            throw std::runtime_error("the root process is gone");
-        }
-    }
-    // spins while the job is active, sleeps between probes after 1 s of waiting (the reference's "turbo off")
-    template <typename Pred> void waitFor(Pred done) {
-        const double t0 = nowMsJob();
-        for (uint32_t i = 0; !done(); i++) {
-            if ((i & 1023u) == 1023u) {
-                checkPeers();
-                if (nowMsJob() - t0 > 1000.0) usleep(200);
-            }
-        }
-    }
-    static double nowMsJob() {
-        using namespace std::chrono;
-        return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
-    }
-    void barrier() {   // all ranks, bootstrap only
-        barriers++;
-        ctl->arrived.fetch_add(1);
-        const uint32_t target = barriers * nRanks;
-        waitFor([&] { return ctl->arrived.load() >= target; });
-    }
-    // root: publish a command after every worker has finished the previous one
-    void issue(uint32_t op, const int32_t *tokens, uint32_t n, uint32_t pos, float temperature = 0.f, float topp = 0.f) {
-        if (nRanks == 1) return;
-        const uint32_t cur = ctl->seq.load();
-        waitFor([&] { for (uint32_t r = 1; r < nRanks; r++) if (ctl->ack[r].load() != cur) return false; return true; });
-        ctl->op = op; ctl->n = n; ctl->pos = pos; ctl->temperature = temperature; ctl->topp = topp;
-        for (uint32_t i = 0; i < n && i < kCtrlTokens; i++) ctl->tokens[i] = tokens[i];
-        ctl->seq.store(cur + 1, std::memory_order_release);
-    }
-};
-
 struct App {
     Args args;
-    Job &job;
+    TpJob &job;
     NativeEngine engine;
     Tokenizer tokenizer;
     Sampler sampler;
-    App(const Args &a, Job &j)
+    TpEngine tp;
+    App(const Args &a, TpJob &j)
         : args(a), job(j), engine(a.model, a.maxSeqLen, a.gpuIndex + (int)j.rank, j.rank, j.nRanks, j.tag, [&j] { j.barrier(); }),
           tokenizer(a.tokenizer),
-          sampler(std::min<uint32_t>(tokenizer.vocabSize(), engine.header().vocabSize), a.temperature, a.topp, a.seed) {
+          sampler(std::min<uint32_t>(tokenizer.vocabSize(), engine.header().vocabSize), a.temperature, a.topp, a.seed), tp{engine, j} {
         // sampling ranges over the tokenizer's vocabulary (reference src/app.cpp:243-246); padded embedding rows never win
         engine.setVocabLimit(tokenizer.vocabSize());
-        if (j.nRanks > 1) engine.seedSampler(a.seed);   // device sampler: every rank draws the same token from the same stream
     }
 
-    void prefill(const std::vector<int32_t> &tokens, uint32_t pos) {
-        for (size_t i = 0; i < tokens.size(); i += 192) {   // one control packet per tensor-core chunk
-            const uint32_t n = (uint32_t)std::min<size_t>(192, tokens.size() - i);
-            job.issue(OP_PREFILL, tokens.data() + i, n, pos + (uint32_t)i);
-            engine.prefill(std::vector<int32_t>(tokens.begin() + i, tokens.begin() + i + n), pos + (uint32_t)i);
-        }
-    }
+    void prefill(const std::vector<int32_t> &tokens, uint32_t pos) { tp.prefill(tokens, pos); }
 
     int32_t next(int32_t token, uint32_t pos) {
-        if (sampler.temperature() == 0.f) {
-            job.issue(OP_STEP_GREEDY, &token, 1, pos);
-            return engine.stepGreedy(token, pos);
-        }
-        if (job.nRanks > 1) {   // logits stay sharded on the devices: temperature / top-p on the device
-            job.issue(OP_STEP_SAMPLED, &token, 1, pos, sampler.temperature(), args.topp);
-            return engine.stepSampled(token, pos, sampler.temperature(), args.topp);
-        }
+        if (sampler.temperature() == 0.f) return tp.stepGreedy(token, pos);
+        if (job.nRanks > 1) return tp.stepSampled(token, pos, sampler, args.topp);   // logits stay sharded on the devices
         const float *logits = engine.step(token, pos);
         std::vector<float> tmp(logits, logits + std::min<uint32_t>(tokenizer.vocabSize(), engine.header().vocabSize));
         return sampler.sample(tmp.data());
     }
 };
-
-// ranks >= 1: mirror the root's engine calls until OP_EXIT (reference: runWorkerApp, src/app.cpp:306-365)
-int workerMain(const Args &a, Job &job) {
-    try {
-        NativeEngine engine(a.model, a.maxSeqLen, a.gpuIndex + (int)job.rank, job.rank, job.nRanks, job.tag, [&job] { job.barrier(); });
-        {
-            Tokenizer tok(a.tokenizer);      // only for the vocabulary limit of the greedy arg-max (must match the root)
-            engine.setVocabLimit(tok.vocabSize());
-        }
-        engine.seedSampler(a.seed);
-        job.barrier();                       // "weights loaded" on every rank
-        uint32_t mine = 0;
-        while (true) {
-            job.waitFor([&] { return job.ctl->seq.load(std::memory_order_acquire) != mine; });
-            mine++;
-            const Control &c = *job.ctl;
-            if (c.op == OP_EXIT) break;
-            if (c.op == OP_PREFILL) engine.prefill(std::vector<int32_t>(c.tokens, c.tokens + c.n), c.pos);
-            else if (c.op == OP_STEP_GREEDY) engine.stepGreedy(c.tokens[0], c.pos);
-            else if (c.op == OP_STEP_SAMPLED) engine.stepSampled(c.tokens[0], c.pos, c.temperature, c.topp);
-            if (c.op == OP_PREFILL) engine.synchronize();
-            job.ctl->ack[job.rank].store(mine, std::memory_order_release);
-        }
-        job.ctl->ack[job.rank].store(mine, std::memory_order_release);
-        return 0;
-    } catch (const std::exception &e) {
-        job.fail(e.what());
-        return 1;
-    }
-}
 
 void inference(App &app) {
     const Args &a = app.args;
@@ -235,7 +128,7 @@ void inference(App &app) {
     if (nIn > h.seqLen) throw std::runtime_error("The number of prompt tokens is greater than the sequence length");
     if (nIn > a.steps) throw std::runtime_error("The number of prompt tokens is greater than the number of steps");
     std::printf("%s\n", a.prompt.c_str());
-    double evalMs = 0, predMs = 0;
+    double evalMs = 0, predMs = 0, syncMs = 0;
     uint32_t pos = 0;
     const uint32_t chunk = 192;   // tokens per tensor-core prefill launch (the reference feeds 32 per forward)
     while (pos + 1 < nIn) {
@@ -245,7 +138,9 @@ void inference(App &app) {
         app.engine.synchronize();
         const double dt = nowMs() - t0;
         evalMs += dt;
-        std::printf("🔷️ Eval%5d ms Sync%5d ms | Sent%6d kB Recv%6d kB | (%u tokens)\n", (int)dt, 0, 0, 0, n);
+        uint64_t sent = 0, recv = 0;
+        app.engine.linkBytes(n, sent, recv);
+        std::printf("🔷️ Eval%5d ms Sync%5d ms | Sent%6d kB Recv%6d kB | (%u tokens)\n", (int)dt, 0, (int)(sent / 1024), (int)(recv / 1024), n);
         pos += n;
     }
     std::fflush(stdout);
@@ -255,11 +150,16 @@ void inference(App &app) {
     uint32_t nPred = 0;
     while (pos < maxPos) {
         const double t0 = nowMs();
+        const uint64_t sync0 = app.engine.syncNs();
         token = app.next(token, pos);
         const double dt = nowMs() - t0;
         predMs += dt;
+        syncMs += (double)(app.engine.syncNs() - sync0) * 1e-6;
+        uint64_t sent = 0, recv = 0;
+        app.engine.linkBytes(1, sent, recv);
         const std::string piece = app.tokenizer.decode(token);
-        std::printf("🔶 Pred%5d ms Sync%5d ms | Sent%6d kB Recv%6d kB | %s\n", (int)dt, 0, 0, 0, piece.empty() ? "~" : piece.c_str());
+        std::printf("🔶 Pred%5d ms Sync%5d ms | Sent%6d kB Recv%6d kB | %s\n", (int)dt, (int)((double)(app.engine.syncNs() - sync0) * 1e-6),
+                    (int)(sent / 1024), (int)(recv / 1024), piece.empty() ? "~" : piece.c_str());
         std::fflush(stdout);
         pos++;
         nPred++;
@@ -269,6 +169,7 @@ void inference(App &app) {
     if (nEval > 0 && evalMs > 0) std::printf("   tokens/s: %3.2f (%3.2f ms/tok)\n", nEval * 1000.0 / evalMs, evalMs / nEval);
     std::printf("Prediction\n    nTokens: %u\n", nPred);
     if (nPred > 0 && predMs > 0) std::printf("   tokens/s: %3.2f (%3.2f ms/tok)\n", nPred * 1000.0 / predMs, predMs / nPred);
+    if (app.job.nRanks > 1 && nPred > 0) std::printf("   syncTime: %3.3f ms/tok waiting for peers inside the fused all-reduces\n", syncMs / nPred);
 }
 
 void perplexity(App &app) {
@@ -364,45 +265,28 @@ int main(int argc, char **argv) {
         if (a.tokenizer.empty()) throw std::runtime_error("Tokenizer is required");
         if (a.bufferFloatType != "q80") throw std::runtime_error("This version supports only Q40 weights with Q80 sync type");
         // ---- tensor-parallel job: fork the workers before CUDA exists in this process ----
-        Job job;
-        job.nRanks = std::min(a.gpus, kMaxRanks);
-        job.rootPid = getpid();
+        TpJob job;
+        job.create(a.gpus);
+        job.reapChildren = true;
         std::vector<pid_t> children;
         if (job.nRanks > 1) {
-            void *p = mmap(nullptr, sizeof(Control), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
-            if (p == MAP_FAILED) throw std::runtime_error("cannot map the control block");
-            job.ctl = new (p) Control();
-            job.tag = "dllama-" + std::to_string((long)getpid()) + "-" + std::to_string((long long)std::time(nullptr));
+            const pid_t rootPid = getpid();
             std::fflush(stdout);
             for (uint32_t r = 1; r < job.nRanks; r++) {
                 const pid_t pid = fork();
                 if (pid < 0) throw std::runtime_error("fork failed");
                 if (pid == 0) {
-                    job.rank = r;
+                    prctl(PR_SET_PDEATHSIG, SIGKILL);
+                    job.rank = r; job.reapChildren = false; job.parentPid = rootPid;
                     std::fclose(stdin);
-                    const int rc = workerMain(a, job);
-                    std::fflush(stdout);
-                    _exit(rc);
+                    _exit(tpWorkerMain(a.model, a.tokenizer, a.maxSeqLen, a.gpuIndex, job));
                 }
                 children.push_back(pid);
             }
         }
         struct Reaper {   // root: tell the workers to leave and collect them, whatever happens
-            Job &job; std::vector<pid_t> &children;
-            ~Reaper() {
-                if (job.nRanks <= 1 || job.rank != 0) return;
-                const uint32_t cur = job.ctl->seq.load();
-                job.ctl->op = OP_EXIT;
-                job.ctl->seq.store(cur + 1, std::memory_order_release);
-                for (pid_t c : children) {
-                    for (int i = 0; i < 3000; i++) {   // 3 s grace, then SIGKILL
-                        int st = 0;
-                        if (waitpid(c, &st, WNOHANG) != 0) { c = 0; break; }
-                        usleep(1000);
-                    }
-                    if (c) { kill(c, SIGKILL); waitpid(c, nullptr, 0); }
-                }
-            }
+            TpJob &job; std::vector<pid_t> &children;
+            ~Reaper() { if (job.nRanks > 1 && job.rank == 0) { job.sendExit(); tpReap(children); } }
         } reaper{job, children};
         std::unique_ptr<App> appPtr;
         try {

@@ -419,6 +419,16 @@ int32_t NativeEngine::stepSampled(int32_t token, uint32_t pos, float temperature
     return next;
 }
 
+uint64_t NativeEngine::syncNs() const { return nRanks_ > 1 ? (uint64_t)dl_engine_sync_ns(impl_->engine) : 0; }
+
+void NativeEngine::linkBytes(uint32_t nTokens, uint64_t &sent, uint64_t &received) const {
+    sent = received = 0;
+    if (nRanks_ <= 1) return;
+    const uint64_t perAr = (uint64_t)nTokens * h_.dim * 8;
+    sent = 2ull * h_.nLayers * perAr * (multicast_ ? 1 : nRanks_ - 1);
+    received = 2ull * h_.nLayers * perAr * (nRanks_ - 1);
+}
+
 void NativeEngine::synchronize() { cudaCheck(cudaStreamSynchronize(impl_->stream), "synchronize"); }
 
 void NativeEngine::setVocabLimit(uint32_t limit) {

@@ -53,6 +53,11 @@ public:
     // n greedy steps back to back on the device without host round trips; returns the generated tokens.
     std::vector<int32_t> decodeGreedy(int32_t firstToken, uint32_t pos, uint32_t nSteps);
     void synchronize();
+    // Traffic / synchronisation accounting of the reference's Eval / Pred lines (src/dllama.cpp:59-66): cumulative ns this rank's
+    // decode kernel waited for its peers inside the fused all-reduces, and (sent, received) NVLink bytes of a forward over nTokens
+    // tokens (2 all-reduces per layer, 8-byte LL words; one multicast store per value when the NVSwitch mapping exists).
+    uint64_t syncNs() const;
+    void linkBytes(uint32_t nTokens, uint64_t &sent, uint64_t &received) const;
     // Greedy decoding on the device ignores vocabulary rows >= limit (tokenizer vocabulary smaller than the embedding table).
     void setVocabLimit(uint32_t limit);
 

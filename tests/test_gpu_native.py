@@ -111,3 +111,56 @@ def test_native_tensor_parallel_two_gpus(tmp_models, name, extra):
     assert len(a) >= 8 and a == b
     c, _ = run("Hello world, the model " * 6, 2)
     assert len(c) >= 8
+
+
+def test_native_api_tensor_parallel_restarts_after_rank_death(tmp_models):
+    """`dllama-api-native --gpus 2`: a supervisor forks one process per GPU (rank 0 serves HTTP). Killing the worker must tear the
+    job down and bring up a new one 3 s later (reference: root retry loop + worker re-listen, src/dllama-api.cpp:616-628)."""
+    import http.client
+    import json
+    import signal
+    import socket
+    import time
+    import psutil
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    m, t = tmp_models["tiny-llama31"]
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    proc = subprocess.Popen([os.path.join(ROOT, "dllama-api-native"), "--model", m, "--tokenizer", t, "--host", "127.0.0.1", "--port", str(port),
+                             "--gpus", "2", "--temperature", "0"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+
+    def complete():
+        body = {"messages": [{"role": "user", "content": "Hello there"}], "max_tokens": 12, "temperature": 0}
+        for _ in range(300):          # the job (re)starts asynchronously
+            try:
+                c = http.client.HTTPConnection("127.0.0.1", port, timeout=60)
+                c.request("POST", "/v1/chat/completions", body=json.dumps(body), headers={"Content-Type": "application/json"})
+                r = c.getresponse()
+                data = r.read().decode("utf-8")
+                if r.status == 200:
+                    return json.loads(data)["choices"][0]["message"]["content"]
+            except OSError:
+                pass
+            time.sleep(0.2)
+        raise AssertionError("no answer from the server")
+
+    try:
+        first = complete()
+        kids = psutil.Process(proc.pid).children()
+        assert len(kids) == 2                               # rank 0 (HTTP) + rank 1
+        try:
+            worker = [k for k in kids if not k.net_connections(kind="tcp")] or kids[1:]
+        except Exception:
+            worker = sorted(kids, key=lambda k: k.create_time())[1:]      # ranks are forked in order
+        worker[0].send_signal(signal.SIGKILL)
+        time.sleep(1.0)
+        second = complete()                                  # answered by the restarted job
+        assert second == first and len(first) > 0
+        assert {k.pid for k in psutil.Process(proc.pid).children()}.isdisjoint({k.pid for k in kids})
+    finally:
+        for k in psutil.Process(proc.pid).children(recursive=True):
+            k.kill()
+        proc.kill()
+        out = proc.communicate(timeout=20)[0]
+    assert "Retrying in 3 seconds" in out
