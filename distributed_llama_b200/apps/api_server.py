@@ -246,11 +246,24 @@ def main(argv=None) -> int:
         sys.stderr.write(USAGE)
         return 0
     if args.gpus > 1 and os.environ.get("DLLAMA_SPAWNED") != "1" and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        # Supervisor of a tensor-parallel serving job: a rank that loses a peer (control-channel heartbeat, device-side wait timeout)
+        # exits non-zero and torchrun tears the job down; the whole job is then started again after 3 s — the reference's root retry
+        # loop + worker re-listen loop (dllama-api.cpp:616-628, app.cpp:306-365).
         import subprocess
-        port = 29500 + (os.getpid() % 2000)
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
-               "--master-port", str(port), "-m", "distributed_llama_b200.apps.api_server"] + argv
-        return subprocess.call(cmd, env=dict(os.environ, DLLAMA_SPAWNED="1"))
+        attempt = 0
+        while True:
+            port = 29500 + ((os.getpid() + 7 * attempt) % 2000)
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                   "--master-port", str(port), "-m", "distributed_llama_b200.apps.api_server"] + argv
+            try:
+                rc = subprocess.call(cmd, env=dict(os.environ, DLLAMA_SPAWNED="1"))
+            except KeyboardInterrupt:
+                return 130
+            if rc == 0 or rc < 0 or rc == 130:
+                return rc
+            print(f"🚨 Inference error: the tensor-parallel job exited with code {rc}\n🔄 Retrying in 3 seconds...", flush=True)
+            time.sleep(3)
+            attempt += 1
     # the reference retries runInferenceApp forever on connection / executor errors (dllama-api.cpp:616-628)
     while True:
         try:
@@ -259,7 +272,7 @@ def main(argv=None) -> int:
         except (ConnectionError, RuntimeError) as e:
             print(f"🚨 Inference error: {e}")
             if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-                return 1          # a lost rank cannot be re-joined from inside the job; the launcher restarts it
+                return 1          # a lost rank cannot be re-joined from inside the job: the supervisor above restarts the whole job
             print("🔄 Retrying in 3 seconds...")
             time.sleep(3)
             args.info = False
