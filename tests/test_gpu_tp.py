@@ -30,13 +30,15 @@ def test_moe_tensor_and_expert_parallel(mode):
     assert "TP_CHECK PASS" in r.stdout and f"moe_mode={mode}" in r.stdout, r.stdout[-3000:]
 
 
-def test_kv_head_replication_more_ranks_than_kv_heads():
-    """4 ranks, 2 KV heads: pairs of ranks share a KV head (the reference cannot run this configuration)."""
-    if torch.cuda.device_count() < 4:
-        pytest.skip("needs 4 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
-           "--master-port", "29644", os.path.join(ROOT, "tools", "tp_check.py"), "tiny-llama-kvrep"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+@pytest.mark.parametrize("n,model,mega", [(4, "tiny-llama-kvrep", "0"), (4, "tiny-llama-kvrep", "1"), (8, "tiny-llama-kvrep8", "1")])
+def test_kv_head_replication_more_ranks_than_kv_heads(n, model, mega):
+    """More ranks than KV heads (4 ranks / 2 KV heads; 8 ranks / 2 KV heads): groups of ranks share a KV head, each with its own
+    query heads (the reference cannot run this configuration). Both decode paths at 4 ranks, the persistent kernel at 8."""
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29644 + n), os.path.join(ROOT, "tools", "tp_check.py"), model]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=dict(os.environ, DL_MEGA=mega))
     assert "TP_CHECK PASS" in r.stdout, r.stdout[-3000:]
 
 
