@@ -46,6 +46,7 @@ struct GemmArgs {
     uint32_t kPair;        // TMA-staged variant: 64-wide k-blocks per MMA step (1 or 2): one barrier round + one commit per step
     uint32_t splitK;       // TMA-staged variant: K is cut into splitK ranges handled by different CTAs (work item = tile x split)
     float *splitScratch;   // [splitK][T][d] f32 partial accumulators
+    uint32_t clusterSplit;  // TMA-staged variant: the splitK CTAs of a row tile form a thread-block cluster and reduce over distributed shared memory
     unsigned int *splitCounters;   // [nTilesM * 4][2], zero-initialised, self-resetting (arrived / done, per 32-row quarter of a tile)
     ArArgs ar;             // GEPI_RESIDUAL_AR: tensor-parallel all-reduce fused into the epilogue (LL words over peer memory)
     uint32_t rawStages;    // TMA-staged variant: depth of the raw q40 ring (2 or 3)
@@ -86,6 +87,27 @@ __device__ __forceinline__ void tmaLoad2d(void *dst, const CUtensorMap *map, uin
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(sAddr(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// ---- thread-block cluster helpers (split-K reduce over distributed shared memory) ----
+__device__ __forceinline__ uint32_t mapaShared(uint32_t localAddr, uint32_t ctaRank) {   // same offset in the peer CTA's shared memory
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(localAddr), "r"(ctaRank));
+    return r;
+}
+__device__ __forceinline__ void stClusterF32(uint32_t clusterAddr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(clusterAddr), "f"(v) : "memory"); }
+__device__ __forceinline__ void arriveRemote(uint32_t clusterAddr) {   // release at cluster scope: this thread's earlier DSMEM stores are visible to the waiter
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(clusterAddr) : "memory");
+}
+__device__ __forceinline__ void gmBarWaitCluster(uint64_t *b, uint32_t parity) {   // acquire at cluster scope (pairs with arriveRemote)
+    uint32_t done = 0;
+    while (true) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(sAddr(b)), "r"(parity) : "memory");
+        if (done) break;
+    }
+}
+__device__ __forceinline__ void clusterSync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // one lane of a converged warp (elect.sync): the predicate form keeps the enclosed tcgen05 operands uniform
 __device__ __forceinline__ bool electOne() {
     uint32_t p;
@@ -348,6 +370,8 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
     uint64_t *rawFull = tmemEmpty + 2;
     uint64_t *rawEmpty = rawFull + kGmRawStagesMax;
     uint32_t *tmemBasePtr = reinterpret_cast<uint32_t *>(rawEmpty + kGmRawStagesMax);
+    uint64_t *freeBar = rawEmpty + kGmRawStagesMax + 1;   // [4 source ranks][4 epilogue warps]: "the rings of rank r are free" (cluster split-K)
+    uint64_t *dataBar = freeBar + 16;                     // [4 epilogue warps]: every peer has delivered its partial sums for my tokens
 
     const uint32_t nkb = a.n / kGmBlockK;
     const uint32_t nkq = (a.n + kGmRawK - 1) / kGmRawK;
@@ -386,6 +410,10 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             gmBarInit(&rawFull[i], 1);
             gmBarInit(&rawEmpty[i], kGmDeqWarps);
         }
+        if (a.clusterSplit) {
+            for (int i = 0; i < 16; i++) gmBarInit(&freeBar[i], 1);
+            for (int i = 0; i < 4; i++) gmBarInit(&dataBar[i], (a.splitK - 1) * 32);   // every lane of the peers' warp q arrives after its stores
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -394,6 +422,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
     }
     tcFenceBefore();
     __syncthreads();
+    if (a.clusterSplit) clusterSync();   // no peer may arrive on (or write into) this CTA before its barriers exist
     tcFenceAfter();
     const uint32_t tmemBase = __shfl_sync(0xffffffffu, *tmemBasePtr, 0);   // warp-uniform for the compiler
 
@@ -513,6 +542,67 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemmQ40TcTmaKernel(const __grid
             const uint32_t f = (grouped ? (tile % a.grpTiles) * kGmBlockM : tile * kGmBlockM) + q * 32 + lane;
             const bool fOk = f < (grouped ? a.grpRows : a.d);
             const uint32_t rowOff = tileTok0(tile);
+            if (splitK > 1 && a.clusterSplit) {
+                // ---- split-K inside a thread-block cluster: the splitK CTAs of this row tile are the ranks of one cluster (rank = ks).
+                // Rank r reduces the tokens [r * per, (r + 1) * per): every other rank stores its partial sums for those tokens
+                // straight into r's shared memory (st.shared::cluster into the A ring, which is idle once r's accumulator is
+                // complete) and arrives on r's mbarrier; r adds them in rank order (deterministic) to its own accumulator columns and
+                // runs the epilogue. No global scratch, no MEMBAR.GPU, no atomics: two DSMEM hops instead of three L2 round trips.
+                const uint32_t per = ((a.T + splitK - 1) / splitK + 15u) & ~15u;      // 16-token granularity = one tcgen05.ld
+                const uint32_t row = q * 32 + lane;
+                const uint32_t recvLocal = sAddr(smem);                                // float recv[splitK - 1][per][128] in the A ring
+                if (lane == 0)
+                    for (uint32_t p = 0; p < splitK; p++)
+                        if (p != ks) arriveRemote(mapaShared(sAddr(&freeBar[ks * 4 + q]), p));   // my MMAs are done: my rings may be overwritten
+                for (uint32_t dp = 1; dp < splitK; dp++) {
+                    const uint32_t p = (ks + dp) % splitK;                             // staggered order: not everybody hits rank 0 first
+                    const uint32_t pBeg = p * per, pEnd = min(a.T, pBeg + per);
+                    gmBarWaitCluster(&freeBar[p * 4 + q], 0);
+                    const uint32_t slot = ks < p ? ks : ks - 1;                        // my place among p's splitK - 1 sources, in rank order
+                    const uint32_t dstBase = mapaShared(recvLocal + (slot * per * kGmBlockM + row) * 4u, p);
+                    for (uint32_t c0 = pBeg; c0 < pEnd; c0 += 16) {
+                        uint32_t r[16];
+                        loadAcc(acc, c0, r);
+#pragma unroll
+                        for (int j = 0; j < 16; j++)
+                            if (c0 + j < pEnd) stClusterF32(dstBase + (c0 + j - pBeg) * (kGmBlockM * 4u), __uint_as_float(r[j]));
+                    }
+                    arriveRemote(mapaShared(sAddr(&dataBar[q]), p));                   // every lane: its own stores are released
+                }
+                const uint32_t tBeg = ks * per, tEnd = min(a.T, tBeg + per);
+                gmBarWaitCluster(&dataBar[q], 0);
+                const float *recv = reinterpret_cast<const float *>(smem);
+                for (uint32_t c0 = tBeg; c0 < tEnd; c0 += 16) {
+                    uint32_t own[16];
+                    loadAcc(acc, c0, own);
+                    float resid[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        resid[j] = (EPI == GEPI_RESIDUAL && c0 + j < tEnd && fOk) ? __ldcg(reinterpret_cast<const float *>(a.out) + (size_t)(c0 + j) * a.outStride + f) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const uint32_t tok = c0 + j;
+                        float v = 0.f;
+                        for (uint32_t r = 0; r < splitK; r++) {                        // rank order, own partial at position ks
+                            if (r == ks) v += __uint_as_float(own[j]);
+                            else if (tok < tEnd) v += recv[(((r < ks ? r : r - 1) * per) + (tok - tBeg)) * kGmBlockM + row];
+                        }
+                        if (EPI == GEPI_SWIGLU_BF16) {
+                            const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+                            if (fOk && tok < tEnd && !(lane & 1))
+                                reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + (f >> 1)] = __float2bfloat16_rn(gateAct(v, a.act) * other);
+                        } else if (fOk && tok < tEnd) {
+                            if (EPI == GEPI_STORE_F32) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = v;
+                            if (EPI == GEPI_RESIDUAL) reinterpret_cast<float *>(a.out)[(size_t)tok * a.outStride + f] = resid[j] + v;
+                            if (EPI == GEPI_STORE_BF16) reinterpret_cast<__nv_bfloat16 *>(a.out)[(size_t)tok * a.outStride + f] = __float2bfloat16_rn(v);
+                        }
+                    }
+                }
+                tcFenceBefore();
+                __syncwarp();
+                if (lane == 0) gmBarArrive(&tmemEmpty[acc]);
+                continue;
+            }
             if (splitK > 1) {
                 // ---- split-K: park the partial accumulator; once all splits of this 32-row quarter have arrived, every split reduces
                 // its own share of the tokens (fixed summation order -> deterministic). All splits of a tile are co-resident (one item
@@ -790,11 +880,16 @@ static int launchGemm(const CUtensorMap &mapB, const CUtensorMap *mapQ, const CU
     cfg.blockDim = dim3(kGmThreads);
     cfg.dynamicSmemBytes = smemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (variant && a.clusterSplit) {   // the splitK CTAs of a row tile = one cluster (consecutive blockIdx.x), reduce over DSMEM
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = a.splitK; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
     if (variant) DL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemmQ40TcTmaKernel<EPI>, mapB, *mapQ, *mapS, a));
     else DL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemmQ40TcKernel<(EPI == GEPI_RESIDUAL_AR ? GEPI_RESIDUAL : EPI)>, mapB, a));
     return 0;
@@ -814,7 +909,7 @@ static bool encode2d(EncodeTiledFn enc, CUtensorMap *map, CUtensorMapDataType ty
 // B ring (>= 2 activation tiles), raw q40 ring. Returns the dynamic shared-memory size, 0 if nothing fits.
 static size_t tmaGeometry(GemmArgs &a) {
     const size_t bTile = (size_t)a.nTile * 128;
-    const size_t budget = 227 * 1024 - 1024 - 512;
+    const size_t budget = 227 * 1024 - 1024 - 1024;   // 1 KB alignment slack + 1 KB of mbarriers
     // Candidates in order of preference: {k-slices per MMA step, A slices, raw stages, minimum B steps}. Two slices per step halve the
     // barrier probes / commits of the issuing warp (it paces the k-loop at <= 128 tokens); then the deeper A ring (two slices per
     // dequant group), then >= 4 k-slices of activations in flight (2 measured ~15 % slower, more than 4 gains nothing).
@@ -824,7 +919,7 @@ static size_t tmaGeometry(GemmArgs &a) {
         if (sscanf(ea, "%u,%u,%u,%u", &gp, &ga, &gr, &gb) == 4 && (gp == 1 || gp == 2) && (ga == 4 || ga == 8) && gr >= 2 && gr <= (unsigned)kGmRawStagesMax &&
             gb >= 2 && gb <= ga / gp) {
             const size_t need = (size_t)ga * kGmATileBytes + (size_t)gr * kGmRawStageBytes + gb * gp * bTile;
-            if (need <= budget) { a.kPair = gp; a.stages = ga; a.rawStages = gr; a.bStages = gb; return need + 1024 + 512; }
+            if (need <= budget) { a.kPair = gp; a.stages = ga; a.rawStages = gr; a.bStages = gb; return need + 1024 + 1024; }
         }
     }
     for (int i = 0; i < 9; i++) {
@@ -836,7 +931,7 @@ static size_t tmaGeometry(GemmArgs &a) {
         const size_t cap = kp == 2 ? nA / 2 : 4;      // released through the A ring's barriers: never deeper than it (in steps)
         if (nb > cap) nb = cap;
         a.kPair = kp; a.stages = nA; a.rawStages = nRaw; a.bStages = (uint32_t)nb;
-        return fixed + nb * bStage + 1024 + 512;
+        return fixed + nb * bStage + 1024 + 1024;
     }
     return 0;
 }
@@ -908,7 +1003,17 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
         // keeps >= 4 raw chunks (1024 of K), and all items must be co-resident (the reduce waits for its sibling splits).
         if (sk > 4) sk = 4;
         if (sk > nkq / 4) sk = nkq / 4;
-        if (nkq < 32 && sk < 4) sk = 1;   // K < 8192: measured at d = 6144 (48 tiles, 3 splits) — the reduce (~6-10 us) eats the shorter k-loop
+        // reduce over distributed shared memory (thread-block cluster) when the receive buffer ((sk - 1) x per x 128 f32) fits into the
+        // idle A ring: ~4 us cheaper than the global-scratch reduce (wo 30.7 -> 26.6 us, w2 43.0 -> 38.9 us at T = 64)
+        const char *clEnv = getenv("DL_GEMM_CLUSTER");
+        auto clusterFits = [&](uint32_t k) {
+            const uint32_t per = ((T + k - 1) / k + 15u) & ~15u;
+            // clusters of 2 or 4 only: clusters of 3 measured much slower (qkv 43.1 vs 32.8 us unsplit), presumably placement inside a GPC
+            return (k == 2 || k == 4) && (size_t)(k - 1) * per * kGmBlockM * 4 <= (size_t)a.stages * kGmATileBytes && !(clEnv && clEnv[0] == '0');
+        };
+        // K < 8192 with fewer than 4 splits (d = 6144: 48 tiles, 3 splits) does not pay: 29.5 vs 29.6 us with the global-scratch reduce,
+        // 43.1 vs 32.8 us with clusters of 3 (T = 64)
+        if (nkq < 32 && sk < 4) sk = 1;
         if (const char *f = getenv("DL_GEMM_SPLITK")) { const uint32_t want = (uint32_t)atoi(f); if (want >= 1 && want < sk) sk = want; }
         if (sk >= 2) {
             const size_t need = (size_t)sk * T * d * sizeof(float);
@@ -921,7 +1026,10 @@ int gemmQ40TcV(int epi, const void *qs, const void *scales, uint32_t d, uint32_t
                 DL_CUDA_CHECK(cudaMalloc(&gSplitCounters, 4096 * sizeof(unsigned int)));
                 DL_CUDA_CHECK(cudaMemset(gSplitCounters, 0, 4096 * sizeof(unsigned int)));
             }
-            if (nTilesM * 8 <= 4096) { a.splitK = sk; a.splitScratch = gSplitScratch; a.splitCounters = gSplitCounters; }
+            if (nTilesM * 8 <= 4096) {
+                a.splitK = sk; a.splitScratch = gSplitScratch; a.splitCounters = gSplitCounters;
+                a.clusterSplit = clusterFits(sk) ? 1u : 0u;
+            }
         }
     }
     const uint32_t nItems = nTilesM * a.splitK;
