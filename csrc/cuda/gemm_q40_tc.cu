@@ -50,7 +50,11 @@ struct GemmArgs {
     unsigned int *splitCounters;   // [nTilesM * 4][2], zero-initialised, self-resetting (arrived / done, per 32-row quarter of a tile)
     ArArgs ar;             // GEPI_RESIDUAL_AR: tensor-parallel all-reduce fused into the epilogue (LL words over peer memory)
     uint32_t rawStages;    // TMA-staged variant: depth of the raw q40 ring (2 or 3)
-    uint32_t debugFlags;   // bit0: skip the proxy fence, bit1: skip the A-tile stores (timing experiments only)
+    // DL_GEMM_DEBUG (timing experiments and the pipeline trace of the TMA-staged variant; never set in production):
+    //   1 skip the proxy fence · 2 skip the A-tile stores · 4 release raw stages late · 8 epilogue waits without back-off
+    //   16 one k-slice per MMA step (kPair = 1) · 32 issue no MMAs after the first · 64 no q40 -> bf16 conversion (32 | 64 = the
+    //   data-movement skeleton) · 256 contiguous raw loads (wrong results) · 512 CTA 0 records %clock64 stamps (tools/trace_gemm.py)
+    uint32_t debugFlags;
     uint32_t act;          // gate activation of GEPI_SWIGLU_BF16 (gHiddenAct)
     // Grouped (mixture-of-experts) mode, TMA-staged variant only: the weight matrix is nGroups stacked [grpRows][n] matrices, the
     // activation / output rows are sorted by group; group g owns rows [grpOffset[g], grpOffset[g] + grpCount[g]) (device arrays
