@@ -302,7 +302,7 @@ int main(int argc, char **argv) {
             std::printf("Tokenizer vocab size (%u) does not match the model vocab size (%u)\n", app.tokenizer.vocabSize(), h.vocabSize);
         std::printf("%s", app.tokenizer.describe().c_str());
         std::printf("%s", describeModelHeader(h).c_str());
-        std::printf("📀 RequiredMemory: %llu MB\n", (unsigned long long)(requiredDeviceBytes(h, 1, 2) / (1024 * 1024)));
+        std::printf("📀 RequiredMemory: %llu MB\n", (unsigned long long)(requiredDeviceBytes(h, job.nRanks, 2) / (1024 * 1024)));
         if (job.nRanks > 1)
             std::printf("🔗 %u GPUs (one process each), all-reduce inside the kernels over %s\n", job.nRanks,
                         app.engine.multicast() ? "the NVSwitch multicast mapping (multimem.st)" : "NVLink peer memory");
